@@ -1,0 +1,125 @@
+// Shared device/host helpers for libacm_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/acm_b200.h"
+
+namespace acm {
+
+// ---- error plumbing (no exceptions across the C boundary) ---------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define ACM_CHECK_ARG(cond, ...)             \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::acm::set_error(__VA_ARGS__);         \
+      return ACM_ERR_BAD_ARG;                \
+    }                                        \
+  } while (0)
+
+#define ACM_LAUNCH_CHECK(name)                                                   \
+  do {                                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    ::acm::count_launch();                                                       \
+    if (e__ != cudaSuccess) {                                                    \
+      ::acm::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));  \
+      return (int)e__;                                                           \
+    }                                                                            \
+  } while (0)
+
+// ---- 8-feature slices: every lane of a row group owns 8 consecutive features ----------
+// bf16: one 16-byte vector; fp32: two.
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+template <typename T>
+struct Slice8;  // raw (register) form of 8 consecutive features of storage type T
+
+template <>
+struct Slice8<__nv_bfloat16> {
+  uint4 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void load_plain(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void to_float(float* f) const { unpack_bf16x8(v, f); }
+  __device__ __forceinline__ static void store(__nv_bfloat16* p, const float* f) {
+    *reinterpret_cast<uint4*>(p) = pack_bf16x8(f);
+  }
+  __device__ __forceinline__ void zero() { v = make_uint4(0, 0, 0, 0); }
+};
+
+template <>
+struct Slice8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void load_plain(const float* p) {
+    a = *reinterpret_cast<const float4*>(p);
+    b = *(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void to_float(float* f) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  __device__ __forceinline__ static void store(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *(reinterpret_cast<float4*>(p) + 1) = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  __device__ __forceinline__ void zero() { a = make_float4(0, 0, 0, 0); b = a; }
+};
+
+// reduce over the LANES lanes of one row group (LANES is a power of two <= 32; groups are
+// aligned, so xor-shuffles stay inside the group)
+template <int LANES>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// layout of the attention parameter pack (see acm_b200.h)
+__host__ __device__ __forceinline__ int pack_off_a(int fp, int k) { return k * fp; }
+__host__ __device__ __forceinline__ int pack_off_avec(int fp) { return 4 * fp; }
+__host__ __device__ __forceinline__ int pack_off_gamma(int fp, int k) { return 4 * fp + 16 + k * fp; }
+__host__ __device__ __forceinline__ int pack_off_beta(int fp, int k) { return 8 * fp + 16 + k * fp; }
+
+constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default, ACM-Geometric/layers.py:21-22
+
+// dispatch helpers -----------------------------------------------------------------------
+#define ACM_DISPATCH_FP(fp, ...)                         \
+  switch (fp) {                                          \
+    case 8: { constexpr int FP = 8; __VA_ARGS__; } break;     \
+    case 16: { constexpr int FP = 16; __VA_ARGS__; } break;   \
+    case 32: { constexpr int FP = 32; __VA_ARGS__; } break;   \
+    case 64: { constexpr int FP = 64; __VA_ARGS__; } break;   \
+    case 128: { constexpr int FP = 128; __VA_ARGS__; } break; \
+    case 256: { constexpr int FP = 256; __VA_ARGS__; } break; \
+    default:                                             \
+      ::acm::set_error("padded feature width %d not in {8,16,32,64,128,256}", (int)(fp)); \
+      return ACM_ERR_UNSUPPORTED;                        \
+  }
+
+}  // namespace acm

@@ -1,0 +1,87 @@
+// C-ABI entry points of the dense feature transforms (forward + both backward products),
+// dispatching to the CUDA-core fp32 path (gemm_simt.cu) or the tcgen05 path (gemm_tc.cu).
+// Reference lines replaced: ACM-Pytorch/models/layers.py:163-165,179-194 (three torch.mm
+// sharing the left operand) and their autograd.
+#include "acm_common.cuh"
+#include "gemm_params.cuh"
+
+namespace acm {
+
+// gemm_tc.cu
+int tc_gemm_fwd(const void* x, int64_t ldx, const void* wcat_t, void* h_lh, void* h_i, int64_t n, int64_t fin,
+                int64_t fp, int relu_lh, cudaStream_t st);
+int tc_gemm_dw(const void* x, int64_t ldx, const void* dh, float* dwcat, int64_t n, int64_t fin, int64_t fp,
+               cudaStream_t st);
+int tc_gemm_dx(const void* dh, const void* wcat, float* dx, int64_t lddx, int64_t n, int64_t fin, int64_t fp,
+               cudaStream_t st);
+}  // namespace acm
+
+extern "C" int acm_gemm_xw_fwd(int impl, int dtype, const void* x, int64_t ldx, const void* wcat, const void* wcat_t,
+                               void* h_lh, void* h_i, int64_t n, int64_t fin, int64_t fp, int relu_lh, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "gemm_xw_fwd: bad dtype %d", dtype);
+  ACM_CHECK_ARG(x && h_lh && h_i, "gemm_xw_fwd: null pointer");
+  ACM_CHECK_ARG(ldx >= fin && fin >= 1, "gemm_xw_fwd: need ldx >= fin >= 1");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == ACM_GEMM_TCGEN05) {
+    ACM_CHECK_ARG(dtype == ACM_BF16, "gemm_xw_fwd: the tcgen05 path computes in bf16; storage dtype must be bf16");
+    ACM_CHECK_ARG(wcat_t, "gemm_xw_fwd: tcgen05 path needs wcat_t");
+    return tc_gemm_fwd(x, ldx, wcat_t, h_lh, h_i, n, fin, fp, relu_lh, st);
+  }
+  ACM_CHECK_ARG(impl == ACM_GEMM_SIMT, "gemm_xw_fwd: unknown impl %d", impl);
+  ACM_CHECK_ARG(wcat, "gemm_xw_fwd: SIMT path needs wcat");
+  GemmParams p{};
+  p.a = x; p.a_rs = ldx; p.a_cs = 1;
+  p.b = wcat; p.b_rs = 3 * fp; p.b_cs = 1;
+  p.c0 = h_lh; p.ldc0 = 2 * fp; p.ncols0 = 2 * fp;
+  p.c1 = h_i; p.ldc1 = fp;
+  p.m = n; p.n = 3 * fp; p.k = fin;
+  p.c_bf16 = (dtype == ACM_BF16); p.relu_cols = relu_lh ? (int)(2 * fp) : 0; p.atomic = 0;
+  return gemm_simt(dtype, p, 1, st);
+}
+
+extern "C" int acm_gemm_bwd_dw(int impl, int dtype, const void* x, int64_t ldx, const void* dh,
+                               float* dwcat, int64_t n, int64_t fin, int64_t fp, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "gemm_bwd_dw: bad dtype %d", dtype);
+  ACM_CHECK_ARG(x && dh && dwcat, "gemm_bwd_dw: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == ACM_GEMM_TCGEN05) {
+    ACM_CHECK_ARG(dtype == ACM_BF16, "gemm_bwd_dw: the tcgen05 path needs bf16 storage");
+    return tc_gemm_dw(x, ldx, dh, dwcat, n, fin, fp, st);
+  }
+  ACM_CHECK_ARG(impl == ACM_GEMM_SIMT, "gemm_bwd_dw: unknown impl %d", impl);
+  GemmParams p{};
+  p.a = x; p.a_rs = 1; p.a_cs = ldx;          // A = X^T : [fin, n]
+  p.b = dh; p.b_rs = 3 * fp; p.b_cs = 1;      // B = dH  : [n, 3fp]
+  p.c0 = dwcat; p.ldc0 = 3 * fp; p.ncols0 = 3 * fp; p.c1 = nullptr; p.ldc1 = 0;
+  p.m = fin; p.n = 3 * fp; p.k = n;
+  p.c_bf16 = 0; p.relu_cols = 0; p.atomic = 1;  // dwcat is zeroed by the caller
+  const int64_t tiles = ((fin + 63) / 64) * ((3 * fp + 63) / 64);
+  int64_t splits = (148 * 8 + tiles - 1) / tiles;
+  const int64_t max_splits = (n + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return gemm_simt(dtype, p, (int)splits, st);
+}
+
+extern "C" int acm_gemm_bwd_dx(int impl, int dtype, const void* dh, const void* wcat, const void* wcat_t, int64_t ldwt,
+                               float* dx, int64_t lddx, int64_t n, int64_t fin, int64_t fp, void* stream) {
+  using namespace acm;
+  (void)wcat_t; (void)ldwt;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "gemm_bwd_dx: bad dtype %d", dtype);
+  ACM_CHECK_ARG(dh && wcat && dx, "gemm_bwd_dx: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == ACM_GEMM_TCGEN05) {
+    ACM_CHECK_ARG(dtype == ACM_BF16, "gemm_bwd_dx: the tcgen05 path needs bf16 storage");
+    return tc_gemm_dx(dh, wcat, dx, lddx, n, fin, fp, st);
+  }
+  ACM_CHECK_ARG(impl == ACM_GEMM_SIMT, "gemm_bwd_dx: unknown impl %d", impl);
+  GemmParams p{};
+  p.a = dh; p.a_rs = 3 * fp; p.a_cs = 1;       // A = dH : [n, 3fp]
+  p.b = wcat; p.b_rs = 1; p.b_cs = 3 * fp;     // B = Wcat^T : [3fp, fin], element (k,j) = wcat[j*3fp + k]
+  p.c0 = dx; p.ldc0 = lddx; p.ncols0 = fin; p.c1 = nullptr; p.ldc1 = 0;
+  p.m = n; p.n = fin; p.k = 3 * fp;
+  p.c_bf16 = 0; p.relu_cols = 0; p.atomic = 0;
+  return gemm_simt(dtype, p, 1, st);
+}

@@ -1,0 +1,326 @@
+// Row-local backward of the channel attention / mix / relu part of the ACM layer
+// (autograd of ACM-Pytorch/models/layers.py:94-152,185-204; math spec in DESIGN.md):
+//   d_alpha_k = c * <G, O_k> ; d_logit = alpha * (d_alpha - <alpha, d_alpha>) ;
+//   d_s = d_logit . att_vec^T / K ; d_att_vec += s^T d_logit / K ; d_z = d_s s (1-s)
+//   d_O_k = c alpha_k G + d_z_k a_k   (through LayerNorm backward when it is live)
+//   d_a_k += O_k^T d_z_k   (LayerNorm(O_k) when live; plus d_gamma, d_beta)
+//   variant 0: d_S_k = d_O_k * [O_k > 0]          variant 1: d_S_k = d_O_k
+// Same lane mapping as the forward kernel (LANES = FP/8 lanes per row, 8 features per
+// lane), no gather: pure streaming, HBM bound.  Parameter gradients are accumulated in
+// registers over a grid-stride loop, reduced through shared memory and flushed with one
+// global atomicAdd per element per block.
+#include "acm_common.cuh"
+
+namespace acm {
+
+struct BwdParams {
+  int64_t n_rows;
+  const float* g;
+  int64_t ldg;
+  const void* o_lh;
+  const void* h_i;
+  const void* o_s;
+  const float* att;
+  const float* sig;
+  const float* pack;
+  int k, ln, variant, f, vec_g;
+  float out_scale;
+  void* t_lh;
+  void* dh_all;
+  void* dos_pre;
+  float* dpack;
+};
+
+constexpr int kBwdWarps = 8;
+
+template <typename T, int FP, int MODE>
+__global__ void __launch_bounds__(kBwdWarps * 32) mix_bwd_kernel(const BwdParams p) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPW = 32 / LANES;
+  constexpr int RPB = RPW * kBwdWarps;
+  constexpr int KMAX = MODE ? 4 : 3;
+  constexpr int TW = 2 * FP;
+
+  extern __shared__ float smem[];
+  float* s_a = smem;                          // [KMAX][FP]
+  float* s_avec = s_a + KMAX * FP;            // [16]
+  float* s_dav = s_avec + 16;                 // [16]  d att_vec
+  float* s_da = s_dav + 16;                   // [KMAX][FP]  d a_k
+  float* s_gam = s_da + KMAX * FP;            // MODE1: gamma [4][FP]
+  float* s_bet = s_gam + (MODE ? 4 * FP : 0); // MODE1: beta  [4][FP]
+  float* s_dg = s_bet + (MODE ? 4 * FP : 0);  // MODE1: d gamma [4][FP]
+  float* s_db = s_dg + (MODE ? 4 * FP : 0);   // MODE1: d beta  [4][FP]
+  float* s_sga = s_db + (MODE ? 4 * FP : 0);  // MODE1: [4] sum_f gamma*a
+
+  const int K = MODE ? p.k : 3;
+  const bool ln = MODE && p.ln;
+  for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) {
+    s_a[i] = p.pack[i];
+    s_da[i] = 0.f;
+  }
+  if (threadIdx.x < 16) {
+    s_avec[threadIdx.x] = p.pack[pack_off_avec(FP) + threadIdx.x];
+    s_dav[threadIdx.x] = 0.f;
+  }
+  if (MODE) {
+    for (int i = threadIdx.x; i < 4 * FP; i += blockDim.x) {
+      s_gam[i] = p.pack[pack_off_gamma(FP, 0) + i];
+      s_bet[i] = p.pack[pack_off_beta(FP, 0) + i];
+      s_dg[i] = 0.f;
+      s_db[i] = 0.f;
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (w < 4) {
+      float sg = 0.f;
+      for (int i = l; i < FP; i += 32) sg += p.pack[pack_off_gamma(FP, w) + i] * p.pack[pack_off_a(FP, w) + i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      if (l == 0) s_sga[w] = sg;
+    }
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int sub = lane / LANES;
+  const int gl = lane % LANES;
+  const int f0 = gl * 8;
+  const float c = p.out_scale;
+  const float inv_k = 1.f / (float)K;
+  const float inv_f = 1.f / (float)p.f;
+
+  float da[KMAX][8];
+  float dgm[MODE ? 4 : 1][8], dbt[MODE ? 4 : 1][8];
+  float dav[16];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) da[k][t] = 0.f;
+#pragma unroll
+  for (int k = 0; k < (MODE ? 4 : 1); ++k)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) dgm[k][t] = dbt[k][t] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dav[i] = 0.f;
+
+  for (int64_t base = (int64_t)blockIdx.x * RPB; base < p.n_rows; base += (int64_t)gridDim.x * RPB) {
+    const int64_t row = base + warp * RPW + sub;
+    const bool valid = row < p.n_rows;
+    float G[8], o[KMAX][8], al[KMAX], sg[KMAX];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) G[t] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      al[k] = 0.f;
+      sg[k] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o[k][t] = 0.f;
+    }
+    if (valid) {
+      const float* gr = p.g + row * p.ldg + f0;
+      if (p.vec_g && f0 + 8 <= p.f) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(gr));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(gr) + 1);
+        G[0] = a.x; G[1] = a.y; G[2] = a.z; G[3] = a.w;
+        G[4] = b.x; G[5] = b.y; G[6] = b.z; G[7] = b.w;
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (f0 + t < p.f) G[t] = __ldg(gr + t);
+      }
+      Slice8<T> a, b, d;
+      const T* ol = reinterpret_cast<const T*>(p.o_lh) + row * TW + f0;
+      a.load(ol);
+      b.load(ol + FP);
+      d.load(reinterpret_cast<const T*>(p.h_i) + row * FP + f0);
+      a.to_float(o[0]);
+      b.to_float(o[1]);
+      d.to_float(o[2]);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) o[2][t] = fmaxf(o[2][t], 0.f);
+      if (MODE && K == 4) {
+        Slice8<T> s4;
+        s4.load(reinterpret_cast<const T*>(p.o_s) + row * FP + f0);
+        s4.to_float(o[KMAX - 1]);
+      }
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+          al[k] = __ldg(p.att + row * K + k);
+          sg[k] = __ldg(p.sig + row * K + k);
+        }
+    }
+    // d_alpha
+    float dal[KMAX], dlog[KMAX], dz[KMAX];
+    float adot = 0.f;
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      float d = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) d = fmaf(G[t], o[k][t], d);
+      dal[k] = c * group_sum<LANES>(d);
+      adot = fmaf(al[k], dal[k], adot);
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) dlog[k] = al[k] * (dal[k] - adot);
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+      float ds = 0.f;
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k)
+        if (k < K) ds = fmaf(dlog[k], s_avec[j * 4 + k], ds);
+      ds *= inv_k;
+      dz[j] = (j < K) ? ds * sg[j] * (1.f - sg[j]) : 0.f;
+      if (gl == 0 && valid) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) dav[j * 4 + k] = fmaf(sg[j], dlog[k] * inv_k, dav[j * 4 + k]);
+      }
+    }
+    // d_O_k (+ parameter gradient partials)
+    float dO[KMAX][8];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (!ln) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          da[k][t] = fmaf(dz[k], o[k][t], da[k][t]);
+          dO[k][t] = fmaf(c * al[k], G[t], dz[k] * s_a[k * FP + f0 + t]);
+        }
+      } else {
+        float s1 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) s1 += o[k][t];
+        const float mu = group_sum<LANES>(s1) * inv_f;
+        float xh[8], s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          xh[t] = (f0 + t < p.f) ? o[k][t] - mu : 0.f;
+          s2 = fmaf(xh[t], xh[t], s2);
+        }
+        const float rstd = 1.f / sqrtf(group_sum<LANES>(s2) * inv_f + kLnEps);
+        float gx = 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          xh[t] *= rstd;
+          gx = fmaf(s_gam[k * FP + f0 + t] * s_a[k * FP + f0 + t], xh[t], gx);
+        }
+        const float m1 = dz[k] * s_sga[k] * inv_f;
+        const float m2 = dz[k] * group_sum<LANES>(gx) * inv_f;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float av = s_a[k * FP + f0 + t];
+          const float gm = s_gam[k * FP + f0 + t];
+          const bool fv = (f0 + t < p.f);
+          const float yln = fv ? fmaf(xh[t], gm, s_bet[k * FP + f0 + t]) : 0.f;
+          da[k][t] = fmaf(dz[k], yln, da[k][t]);
+          dgm[MODE ? k : 0][t] = fmaf(dz[k] * av, xh[t], dgm[MODE ? k : 0][t]);
+          if (fv) dbt[MODE ? k : 0][t] = fmaf(dz[k], av, dbt[MODE ? k : 0][t]);
+          const float dln = fv ? rstd * (dz[k] * gm * av - m1 - xh[t] * m2) : 0.f;
+          dO[k][t] = fmaf(c * al[k], G[t], dln);
+        }
+      }
+    }
+    if (valid) {
+      float out[8];
+      T* tl = reinterpret_cast<T*>(p.t_lh) + row * TW + f0;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) out[t] = (p.variant || o[k][t] > 0.f) ? dO[k][t] : 0.f;
+        Slice8<T>::store(tl + k * FP, out);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) out[t] = (o[2][t] > 0.f) ? dO[2][t] : 0.f;
+      Slice8<T>::store(reinterpret_cast<T*>(p.dh_all) + row * (3 * FP) + 2 * FP + f0, out);
+      if (MODE && K == 4) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) out[t] = (o[KMAX - 1][t] > 0.f) ? dO[KMAX - 1][t] : 0.f;
+        Slice8<T>::store(reinterpret_cast<T*>(p.dos_pre) + row * FP + f0, out);
+      }
+    }
+  }
+
+  // ---- flush parameter gradients: registers -> shared -> one global atomic per element ----
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      atomicAdd(&s_da[k * FP + f0 + t], da[k][t]);
+      if (MODE && ln) {
+        atomicAdd(&s_dg[k * FP + f0 + t], dgm[MODE ? k : 0][t]);
+        atomicAdd(&s_db[k * FP + f0 + t], dbt[MODE ? k : 0][t]);
+      }
+    }
+  if (gl == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) atomicAdd(&s_dav[i], dav[i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) {
+    const float v = s_da[i];
+    if (v != 0.f) atomicAdd(p.dpack + i, v);
+  }
+  if (threadIdx.x < 16) {
+    const float v = s_dav[threadIdx.x];
+    if (v != 0.f) atomicAdd(p.dpack + pack_off_avec(FP) + threadIdx.x, v);
+  }
+  if (MODE && ln) {
+    for (int i = threadIdx.x; i < 4 * FP; i += blockDim.x) {
+      const float v = s_dg[i], w = s_db[i];
+      if (v != 0.f) atomicAdd(p.dpack + pack_off_gamma(FP, 0) + i, v);
+      if (w != 0.f) atomicAdd(p.dpack + pack_off_beta(FP, 0) + i, w);
+    }
+  }
+}
+
+template <typename T, int FP, int MODE>
+static int launch_bwd(const BwdParams& p, cudaStream_t st) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPB = (32 / LANES) * kBwdWarps;
+  int64_t blocks = (p.n_rows + RPB - 1) / RPB;
+  if (blocks == 0) return 0;
+  // persistent-style grid: a few CTAs per SM, grid-stride over rows, so the number of
+  // global atomics per parameter element stays ~ #CTAs
+  const int64_t cap = 148 * (MODE ? 2 : 4);
+  if (blocks > cap) blocks = cap;
+  const size_t nfl = (size_t)(MODE ? 4 : 3) * FP * 2 + 32 + (MODE ? 16 * FP + 4 : 0);
+  const size_t smem = sizeof(float) * nfl;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(mix_bwd_kernel<T, FP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("mix_bwd: cannot raise dynamic shared memory to %zu: %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+  }
+  mix_bwd_kernel<T, FP, MODE><<<(unsigned)blocks, kBwdWarps * 32, smem, st>>>(p);
+  ACM_LAUNCH_CHECK("mix_bwd");
+  return 0;
+}
+
+}  // namespace acm
+
+extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
+                           const float* g, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
+                           const float* att, const float* sig, const float* pack,
+                           int k_channels, int ln_live, int variant, float out_scale,
+                           void* t_lh, void* dh_all, void* dos_pre, float* dpack, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "mix_bwd: bad dtype %d", dtype);
+  ACM_CHECK_ARG(k_channels == 3 || k_channels == 4, "mix_bwd: k_channels must be 3 or 4");
+  ACM_CHECK_ARG(f >= 1 && f <= fp, "mix_bwd: need 1 <= f <= fp");
+  ACM_CHECK_ARG(k_channels == 3 || (o_s && dos_pre), "mix_bwd: 4 channels need o_s and dos_pre");
+  ACM_CHECK_ARG(g && o_lh && h_i && att && sig && pack && t_lh && dh_all && dpack, "mix_bwd: null pointer");
+  BwdParams p;
+  p.n_rows = n_rows; p.g = g; p.ldg = ldg; p.o_lh = o_lh; p.h_i = h_i; p.o_s = o_s; p.att = att; p.sig = sig;
+  p.pack = pack; p.k = k_channels; p.ln = ln_live; p.variant = variant; p.f = f; p.out_scale = out_scale;
+  p.t_lh = t_lh; p.dh_all = dh_all; p.dos_pre = dos_pre; p.dpack = dpack;
+  p.vec_g = (f % 4 == 0) && (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int mode = (k_channels == 4 || ln_live) ? 1 : 0;
+  if (dtype == ACM_BF16) {
+    ACM_DISPATCH_FP(fp, return mode ? launch_bwd<__nv_bfloat16, FP, 1>(p, st) : launch_bwd<__nv_bfloat16, FP, 0>(p, st));
+  } else {
+    ACM_DISPATCH_FP(fp, return mode ? launch_bwd<float, FP, 1>(p, st) : launch_bwd<float, FP, 0>(p, st));
+  }
+  return 0;
+}

@@ -1,0 +1,299 @@
+// Fused forward of the ACM layer: CSR row-parallel aggregation of the [HL|HH] table
+// (one gather per stored edge serves the low-pass AND the high-pass channel) + relu +
+// per-node channel attention (optional LayerNorm, sigmoid, KxK mix, softmax) + weighted sum.
+//
+// Replaces, in one launch, the ~25 ATen launches of
+//   ACM-Pytorch/models/layers.py:176-204 + attention3/attention4 (94-152)
+//   (ACM-Geometric/layers.py:57-116; the LayerNorm branch is live there).
+//
+// Mapping: a row is owned by a group of LANES = FP/8 lanes; each lane owns the same 8
+// features of every channel, so the whole epilogue is lane-local except K (or 3K with
+// LayerNorm) group reductions.  Per edge a lane issues two 16-byte loads (bf16) from the
+// neighbour's table row: features [8g,8g+8) of HL and of HH.  Accumulation is fp32.
+#include "acm_common.cuh"
+
+namespace acm {
+
+struct FwdParams {
+  int64_t n_rows, row0;
+  const int64_t* rowptr;
+  const int32_t* col;
+  const float* val;
+  const float* rowscale;
+  const void* table;
+  const void* h_i;
+  const void* o_s;
+  const float* pack;
+  int k, ln, variant, f, vec_y;
+  float out_scale;
+  float* y;
+  int64_t ldy;
+  void* o_save;
+  float* att;
+  float* sig;
+};
+
+constexpr int kFwdWarps = 8;
+constexpr int kUnroll = 4;
+
+template <typename T, int FP, int MODE>
+__global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdParams p) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPW = 32 / LANES;
+  constexpr int KMAX = MODE ? 4 : 3;
+  constexpr int TW = 2 * FP;  // table row width (elements)
+
+  extern __shared__ float smem[];
+  float* s_a = smem;                 // [KMAX][FP]   a_k
+  float* s_avec = s_a + KMAX * FP;   // [16]
+  float* s_ga = s_avec + 16;         // MODE 1: [4][FP] gamma*a
+  float* s_sc = s_ga + (MODE ? 4 * FP : 0);  // MODE 1: [8] sum(beta*a) per channel
+
+  const int K = MODE ? p.k : 3;
+  for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) s_a[i] = p.pack[i];
+  if (threadIdx.x < 16) s_avec[threadIdx.x] = p.pack[pack_off_avec(FP) + threadIdx.x];
+  if (MODE) {
+    if (p.ln) {
+      for (int i = threadIdx.x; i < 4 * FP; i += blockDim.x)
+        s_ga[i] = p.pack[pack_off_gamma(FP, 0) + i] * p.pack[i];
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      if (w < 4) {
+        float sb = 0.f;
+        for (int i = l; i < FP; i += 32) sb += p.pack[pack_off_beta(FP, w) + i] * p.pack[pack_off_a(FP, w) + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        if (l == 0) s_sc[w] = sb;
+      }
+    }
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int sub = lane / LANES;
+  const int gl = lane % LANES;
+  const int64_t row = ((int64_t)blockIdx.x * kFwdWarps + warp) * RPW + sub;
+  const bool valid = row < p.n_rows;
+
+  int64_t e = 0, e1 = 0;
+  if (valid) {
+    e = __ldg(p.rowptr + row);
+    e1 = __ldg(p.rowptr + row + 1);
+  }
+  const T* __restrict__ tab = reinterpret_cast<const T*>(p.table) + gl * 8;
+  const int32_t* __restrict__ col = p.col;
+  const float* __restrict__ val = p.val;
+
+  float accL[8], accH[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) accL[t] = accH[t] = 0.f;
+
+  // ---- gather loop: kUnroll independent neighbour rows in flight per lane ----------------
+  for (; e + kUnroll <= e1; e += kUnroll) {
+    int32_t c[kUnroll];
+    float w[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      c[u] = __ldg(col + e + u);
+      w[u] = val ? __ldg(val + e + u) : 1.f;
+    }
+    Slice8<T> vl[kUnroll], vh[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const T* r = tab + (int64_t)c[u] * TW;
+      vl[u].load(r);
+      vh[u].load(r + FP);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      float fl[8], fh[8];
+      vl[u].to_float(fl);
+      vh[u].to_float(fh);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        accL[t] = fmaf(w[u], fl[t], accL[t]);
+        accH[t] = fmaf(w[u], fh[t], accH[t]);
+      }
+    }
+  }
+  for (; e < e1; ++e) {
+    const int32_t c = __ldg(col + e);
+    const float w = val ? __ldg(val + e) : 1.f;
+    const T* r = tab + (int64_t)c * TW;
+    Slice8<T> vl, vh;
+    vl.load(r);
+    vh.load(r + FP);
+    float fl[8], fh[8];
+    vl.to_float(fl);
+    vh.to_float(fh);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      accL[t] = fmaf(w, fl[t], accL[t]);
+      accH[t] = fmaf(w, fh[t], accH[t]);
+    }
+  }
+
+  // ---- epilogue: channels, attention, mix --------------------------------------------------
+  float o[KMAX][8];
+  {
+    float hs[8], hi[8];
+    if (valid) {
+      Slice8<T> a, b;
+      a.load(tab + (p.row0 + row) * TW + FP);
+      b.load(reinterpret_cast<const T*>(p.h_i) + row * FP + gl * 8);
+      a.to_float(hs);
+      b.to_float(hi);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) hs[t] = hi[t] = 0.f;
+    }
+    const float rs = (valid && p.rowscale) ? __ldg(p.rowscale + row) : 1.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float sl = rs * accL[t];
+      float sh = hs[t] - rs * accH[t];
+      if (!p.variant) {
+        sl = fmaxf(sl, 0.f);
+        sh = fmaxf(sh, 0.f);
+      }
+      o[0][t] = sl;
+      o[1][t] = sh;
+      o[2][t] = fmaxf(hi[t], 0.f);
+    }
+    if (MODE) {
+      if (K == 4 && valid) {
+        Slice8<T> s4;
+        s4.load(reinterpret_cast<const T*>(p.o_s) + row * FP + gl * 8);
+        s4.to_float(o[KMAX - 1]);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[KMAX - 1][t] = 0.f;
+      }
+    }
+  }
+
+  float z[KMAX];
+  const bool ln = MODE && p.ln;
+  const float inv_f = 1.f / (float)p.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    float dot = 0.f;
+    if (!ln) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) dot = fmaf(o[k][t], s_a[k * FP + gl * 8 + t], dot);
+      z[k] = group_sum<LANES>(dot);
+    } else {
+      float s1 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s1 += o[k][t];
+      const float mu = group_sum<LANES>(s1) * inv_f;
+      float s2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d = (gl * 8 + t < p.f) ? o[k][t] - mu : 0.f;
+        s2 = fmaf(d, d, s2);
+        dot = fmaf(d, s_ga[k * FP + gl * 8 + t], dot);
+      }
+      const float var = group_sum<LANES>(s2) * inv_f;
+      dot = group_sum<LANES>(dot);
+      z[k] = dot / sqrtf(var + kLnEps) + s_sc[k];
+    }
+  }
+  float s[KMAX], a[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) s[k] = sigmoidf_acc(z[k]);
+  float mx = -INFINITY;
+  const float inv_k = 1.f / (float)K;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j < K) l = fmaf(s[j], s_avec[j * 4 + k], l);
+    a[k] = (k < K) ? l * inv_k : -INFINITY;
+    mx = fmaxf(mx, a[k]);
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    a[k] = (k < K) ? expf(a[k] - mx) : 0.f;
+    den += a[k];
+  }
+  const float rden = 1.f / den;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) a[k] *= rden;
+
+  if (!valid) return;
+
+  float yv[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float acc = a[0] * o[0][t];
+#pragma unroll
+    for (int k = 1; k < KMAX; ++k) acc = fmaf(a[k], o[k][t], acc);
+    yv[t] = p.out_scale * acc;
+  }
+  const int f0 = gl * 8;
+  float* yr = p.y + row * p.ldy + f0;
+  if (p.vec_y && f0 + 8 <= p.f) {
+    *reinterpret_cast<float4*>(yr) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+    *reinterpret_cast<float4*>(yr + 4) = make_float4(yv[4], yv[5], yv[6], yv[7]);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (f0 + t < p.f) yr[t] = yv[t];
+  }
+  if (p.o_save) {
+    T* os = reinterpret_cast<T*>(p.o_save) + row * TW + f0;
+    Slice8<T>::store(os, o[0]);
+    Slice8<T>::store(os + FP, o[1]);
+  }
+  if (gl == 0) {
+    for (int k = 0; k < K; ++k) {
+      p.att[row * K + k] = a[k];
+      if (p.sig) p.sig[row * K + k] = s[k];
+    }
+  }
+}
+
+template <typename T, int FP, int MODE>
+static int launch_fwd(const FwdParams& p, cudaStream_t st) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPB = (32 / LANES) * kFwdWarps;
+  const int64_t blocks = (p.n_rows + RPB - 1) / RPB;
+  if (blocks == 0) return 0;
+  ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_mix_fwd: too many rows for one launch");
+  const size_t smem = sizeof(float) * ((MODE ? 4 : 3) * FP + 16 + (MODE ? 4 * FP + 8 : 0));
+  spmm_mix_fwd_kernel<T, FP, MODE><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
+  ACM_LAUNCH_CHECK("spmm_mix_fwd");
+  return 0;
+}
+
+}  // namespace acm
+
+extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
+                                const int64_t* rowptr, const int32_t* col, const float* val, const float* rowscale,
+                                const void* table, const void* h_i, const void* o_s,
+                                const float* pack, int k_channels, int ln_live, int variant, float out_scale,
+                                float* y, int64_t ldy, void* o_save, float* att, float* sig, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_mix_fwd: bad dtype %d", dtype);
+  ACM_CHECK_ARG(k_channels == 3 || k_channels == 4, "spmm_mix_fwd: k_channels must be 3 or 4");
+  ACM_CHECK_ARG(f >= 1 && f <= fp, "spmm_mix_fwd: need 1 <= f <= fp");
+  ACM_CHECK_ARG(k_channels == 3 || o_s != nullptr, "spmm_mix_fwd: 4 channels need o_s");
+  ACM_CHECK_ARG(rowptr && col && table && h_i && pack && y && att, "spmm_mix_fwd: null pointer");
+  FwdParams p;
+  p.n_rows = n_rows; p.row0 = row0; p.rowptr = rowptr; p.col = col; p.val = val; p.rowscale = rowscale;
+  p.table = table; p.h_i = h_i; p.o_s = o_s; p.pack = pack; p.k = k_channels; p.ln = ln_live;
+  p.variant = variant; p.f = f; p.out_scale = out_scale; p.y = y; p.ldy = ldy; p.o_save = o_save;
+  p.att = att; p.sig = sig;
+  p.vec_y = (f % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int mode = (k_channels == 4 || ln_live) ? 1 : 0;
+  if (dtype == ACM_BF16) {
+    ACM_DISPATCH_FP(fp, return mode ? launch_fwd<__nv_bfloat16, FP, 1>(p, st) : launch_fwd<__nv_bfloat16, FP, 0>(p, st));
+  } else {
+    ACM_DISPATCH_FP(fp, return mode ? launch_fwd<float, FP, 1>(p, st) : launch_fwd<float, FP, 0>(p, st));
+  }
+  return 0;
+}

@@ -1,0 +1,211 @@
+// Transposed aggregation for the backward pass and the plain single-table aggregation
+// used by the structure channel.
+//
+//  acm_spmm_t_bwd : autograd of torch.spmm(adj_low, .) and torch.spmm(adj_high, .)
+//                   (ACM-Pytorch/models/layers.py:178-193):
+//                     dHL = A_low^T dS_L ,  dHH = dS_H - A_low^T dS_H
+//                   one gather of the [dS_L|dS_H] row per stored edge of A_low^T.
+//  acm_spmm_plain : relu(mm(adj_low_unnormalized, struc_low)) (layers.py:207-209) and the
+//                   transpose product of its backward.
+#include "acm_common.cuh"
+
+namespace acm {
+
+constexpr int kTWarps = 8;
+constexpr int kTUnroll = 4;
+
+template <typename T, int FP>
+__global__ void __launch_bounds__(kTWarps * 32)
+spmm_t_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+              const float* __restrict__ val, const T* __restrict__ table, const T* __restrict__ ptab,
+              T* __restrict__ dh_all) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPW = 32 / LANES;
+  constexpr int TW = 2 * FP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LANES, gl = lane % LANES;
+  const int64_t row = ((int64_t)blockIdx.x * kTWarps + warp) * RPW + sub;
+  if (row >= n_rows) return;  // no cross-lane traffic in this kernel
+  int64_t e = __ldg(rowptr + row);
+  const int64_t e1 = __ldg(rowptr + row + 1);
+  const T* tab = table + gl * 8;
+  float accL[8], accH[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) accL[t] = accH[t] = 0.f;
+  for (; e + kTUnroll <= e1; e += kTUnroll) {
+    int32_t c[kTUnroll];
+    float w[kTUnroll];
+#pragma unroll
+    for (int u = 0; u < kTUnroll; ++u) {
+      c[u] = __ldg(col + e + u);
+      w[u] = val ? __ldg(val + e + u) : 1.f;
+    }
+    Slice8<T> vl[kTUnroll], vh[kTUnroll];
+#pragma unroll
+    for (int u = 0; u < kTUnroll; ++u) {
+      const T* r = tab + (int64_t)c[u] * TW;
+      vl[u].load(r);
+      vh[u].load(r + FP);
+    }
+#pragma unroll
+    for (int u = 0; u < kTUnroll; ++u) {
+      float fl[8], fh[8];
+      vl[u].to_float(fl);
+      vh[u].to_float(fh);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        accL[t] = fmaf(w[u], fl[t], accL[t]);
+        accH[t] = fmaf(w[u], fh[t], accH[t]);
+      }
+    }
+  }
+  for (; e < e1; ++e) {
+    const int32_t c = __ldg(col + e);
+    const float w = val ? __ldg(val + e) : 1.f;
+    const T* r = tab + (int64_t)c * TW;
+    Slice8<T> vl, vh;
+    vl.load(r);
+    vh.load(r + FP);
+    float fl[8], fh[8];
+    vl.to_float(fl);
+    vh.to_float(fh);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      accL[t] = fmaf(w, fl[t], accL[t]);
+      accH[t] = fmaf(w, fh[t], accH[t]);
+    }
+  }
+  float self[8];
+  {
+    Slice8<T> s;
+    s.load(tab + (row0 + row) * TW + FP);
+    s.to_float(self);
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) accH[t] = self[t] - accH[t];
+  if (ptab) {  // variant 1: relu sits before the aggregation -> mask with the forward table
+    Slice8<T> a, b;
+    float pl[8], ph[8];
+    a.load(ptab + row * TW + gl * 8);
+    b.load(ptab + row * TW + FP + gl * 8);
+    a.to_float(pl);
+    b.to_float(ph);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (!(pl[t] > 0.f)) accL[t] = 0.f;
+      if (!(ph[t] > 0.f)) accH[t] = 0.f;
+    }
+  }
+  T* out = dh_all + row * (3 * FP) + gl * 8;
+  Slice8<T>::store(out, accL);
+  Slice8<T>::store(out + FP, accH);
+}
+
+template <typename T, typename TO, int FP>
+__global__ void __launch_bounds__(kTWarps * 32)
+spmm_plain_kernel(int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                  const float* __restrict__ val, const T* __restrict__ table, TO* __restrict__ out,
+                  int64_t ld_out, int f_out, int relu) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPW = 32 / LANES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LANES, gl = lane % LANES;
+  const int64_t row = ((int64_t)blockIdx.x * kTWarps + warp) * RPW + sub;
+  if (row >= n_rows) return;
+  int64_t e = __ldg(rowptr + row);
+  const int64_t e1 = __ldg(rowptr + row + 1);
+  const T* tab = table + gl * 8;
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  for (; e + kTUnroll <= e1; e += kTUnroll) {
+    int32_t c[kTUnroll];
+    float w[kTUnroll];
+#pragma unroll
+    for (int u = 0; u < kTUnroll; ++u) {
+      c[u] = __ldg(col + e + u);
+      w[u] = val ? __ldg(val + e + u) : 1.f;
+    }
+    Slice8<T> v[kTUnroll];
+#pragma unroll
+    for (int u = 0; u < kTUnroll; ++u) v[u].load(tab + (int64_t)c[u] * FP);
+#pragma unroll
+    for (int u = 0; u < kTUnroll; ++u) {
+      float f[8];
+      v[u].to_float(f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] = fmaf(w[u], f[t], acc[t]);
+    }
+  }
+  for (; e < e1; ++e) {
+    const int32_t c = __ldg(col + e);
+    const float w = val ? __ldg(val + e) : 1.f;
+    Slice8<T> v;
+    v.load(tab + (int64_t)c * FP);
+    float f[8];
+    v.to_float(f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = fmaf(w, f[t], acc[t]);
+  }
+  TO* o = out + row * ld_out + gl * 8;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float v = relu ? fmaxf(acc[t], 0.f) : acc[t];
+    if (gl * 8 + t < f_out) {
+      if constexpr (sizeof(TO) == 2) o[t] = __float2bfloat16_rn(v);
+      else o[t] = v;
+    }
+  }
+}
+
+}  // namespace acm
+
+extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
+                              const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
+                              const void* t_table, const void* p_table, void* dh_all, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_t_bwd: bad dtype %d", dtype);
+  ACM_CHECK_ARG(rowptr_t && col_t && t_table && dh_all, "spmm_t_bwd: null pointer");
+  if (n_rows == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define ACM_T_LAUNCH(TT)                                                                           \
+  ACM_DISPATCH_FP(fp, {                                                                            \
+    constexpr int RPB = (32 / (FP / 8)) * kTWarps;                                                 \
+    const int64_t blocks = (n_rows + RPB - 1) / RPB;                                               \
+    ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_t_bwd: too many rows");                              \
+    spmm_t_kernel<TT, FP><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                              \
+        n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all); \
+  })
+  if (dtype == ACM_BF16) { ACM_T_LAUNCH(__nv_bfloat16); } else { ACM_T_LAUNCH(float); }
+#undef ACM_T_LAUNCH
+  ACM_LAUNCH_CHECK("spmm_t_bwd");
+  return 0;
+}
+
+extern "C" int acm_spmm_plain(int dtype, int out_dtype, int fp, int64_t n_rows,
+                              const int64_t* rowptr, const int32_t* col, const float* val,
+                              const void* table, void* out, int64_t ld_out, int f_out, int relu, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_plain: bad dtype %d", dtype);
+  ACM_CHECK_ARG(out_dtype == ACM_F32 || out_dtype == ACM_BF16, "spmm_plain: bad out dtype %d", out_dtype);
+  ACM_CHECK_ARG(rowptr && col && table && out, "spmm_plain: null pointer");
+  ACM_CHECK_ARG(f_out >= 1 && f_out <= fp, "spmm_plain: need 1 <= f_out <= fp");
+  if (n_rows == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define ACM_P_LAUNCH(TT, TO)                                                                  \
+  ACM_DISPATCH_FP(fp, {                                                                       \
+    constexpr int RPB = (32 / (FP / 8)) * kTWarps;                                            \
+    const int64_t blocks = (n_rows + RPB - 1) / RPB;                                          \
+    ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_plain: too many rows");                         \
+    spmm_plain_kernel<TT, TO, FP><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                 \
+        n_rows, rowptr, col, val, (const TT*)table, (TO*)out, ld_out, f_out, relu);           \
+  })
+  if (dtype == ACM_BF16) {
+    if (out_dtype == ACM_BF16) { ACM_P_LAUNCH(__nv_bfloat16, __nv_bfloat16); } else { ACM_P_LAUNCH(__nv_bfloat16, float); }
+  } else {
+    if (out_dtype == ACM_BF16) { ACM_P_LAUNCH(float, __nv_bfloat16); } else { ACM_P_LAUNCH(float, float); }
+  }
+#undef ACM_P_LAUNCH
+  ACM_LAUNCH_CHECK("spmm_plain");
+  return 0;
+}

@@ -1,0 +1,63 @@
+"""1-D row (node) partition of the ACM layer over the GPUs of one box.
+
+The reference is single-device.  Rows of ``A_low`` (destination nodes) are independent;
+each output row needs the table rows of its neighbours, so the one data-path exchange per
+aggregation is an all-gather of the operand table -- ``[HL|HH]`` forward, ``[dS_L|dS_H]``
+backward -- over NVLink (NCCL), plus an all-reduce of the (replicated) parameter
+gradients.  For uniform random graphs the halo is ~all nodes (each of 8 ranks references
+92 % of them at mean degree 20), so a full all-gather is the right collective.
+
+One process per GPU (torchrun); rank r owns rows [r*rows_per_rank, min(N,(r+1)*rows_per_rank)).
+Works with the gloo backend on CPU tensors too, which is how the host logic is tested.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class RowPartition:
+    def __init__(self, n_global: int, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_global = int(n_global)
+        self.rows_per_rank = (self.n_global + self.world - 1) // self.world
+        self.r0 = min(self.n_global, self.rank * self.rows_per_rank)
+        self.r1 = min(self.n_global, self.r0 + self.rows_per_rank)
+        self.n_local = self.r1 - self.r0
+        self.bytes_gathered = 0
+
+    def bounds(self, rank):
+        r0 = min(self.n_global, rank * self.rows_per_rank)
+        return r0, min(self.n_global, r0 + self.rows_per_rank)
+
+    def all_gather_rows(self, local: torch.Tensor) -> torch.Tensor:
+        """[n_local, W] per rank -> [world*rows_per_rank, W] on every rank; row g of the result
+        is global node g (ranks are padded to rows_per_rank rows; pad rows are never indexed
+        because column ids are < n_global)."""
+        w = local.shape[1]
+        if local.shape[0] != self.n_local:
+            raise ValueError(f"expected {self.n_local} local rows, got {local.shape[0]}")
+        if self.n_local != self.rows_per_rank:
+            pad = torch.zeros(self.rows_per_rank, w, dtype=local.dtype, device=local.device)
+            pad[: self.n_local] = local
+            local = pad
+        out = torch.empty(self.world * self.rows_per_rank, w, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
+        self.bytes_gathered += out.numel() * out.element_size()
+        return out
+
+    def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+def attach(model, part: RowPartition):
+    """Mark every ACM layer of ``model`` as row-partitioned (parameters stay replicated: all
+    ranks seed identically, SURVEY.md 8e "Process model")."""
+    from .layers import GraphConvolution
+    for m in model.modules():
+        if isinstance(m, GraphConvolution):
+            m.acm_dist = part
+    return model

@@ -1,0 +1,245 @@
+"""Autograd boundary of the ACM layer: one ``torch.autograd.Function`` per layer call whose
+forward and backward are sequences of libacm_b200 launches on the current CUDA stream.
+
+Math (validated against the reference, SURVEY.md section 8a / DESIGN.md):
+  fwd  [HL|HH|HI] = X [W_L|W_H|W_I]
+       variant 0: O_L = relu(A HL), O_H = relu(HH - A HH)        (layers.py:188-193)
+       variant 1: O_L = A relu(HL), O_H = relu(HH) - A relu(HH)  (layers.py:178-184)
+       O_I = relu(HI) ; [O_S = relu(A_raw S)] ; att = softmax(sigmoid([LN](O_k).a_k) Avec / K)
+       Y = c * sum_k att_k O_k       (c = 3, or 1 with the structure channel; layers.py:200-232)
+  bwd  mix_bwd (row local) -> transposed aggregation -> dWcat = X^T dH, dX = dH Wcat^T
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .operator import AcmOperator
+
+_FP_CHOICES = (8, 16, 32, 64, 128, 256)
+
+
+def padded_width(f: int) -> int:
+    for c in _FP_CHOICES:
+        if f <= c:
+            return c
+    raise NotImplementedError(f"out_features={f} > 256 is not supported by the fused ACM kernels yet")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class LayerConfig:
+    variant: bool = False
+    k_channels: int = 3
+    ln_live: bool = False
+    out_scale: float = 3.0
+    dtype: str = "bf16"        # storage of feature tables: "bf16" | "fp32" (accumulation is fp32)
+    gemm: str = "auto"         # "simt" | "tcgen05" | "auto"
+    dist: Optional[object] = None   # acm_gnn_b200.dist.RowPartition or None
+
+    def storage(self):
+        return (torch.bfloat16, _lib.ACM_BF16) if self.dtype == "bf16" else (torch.float32, _lib.ACM_F32)
+
+    def gemm_impl(self, fin: int):
+        g = self.gemm
+        if g == "auto":
+            g = os.environ.get("ACMB200_GEMM", "auto")
+        if g == "auto":
+            g = "tcgen05" if (self.dtype == "bf16" and tc_available()) else "simt"
+        if g == "tcgen05" and self.dtype != "bf16":
+            raise ValueError("the tcgen05 GEMM path computes in bf16; use dtype='bf16' or gemm='simt'")
+        return _lib.GEMM_TCGEN05 if g == "tcgen05" else _lib.GEMM_SIMT
+
+
+_TC_OK = None
+
+
+def tc_available() -> bool:
+    """Whether the tcgen05 GEMM kernels are compiled into the library (probe once)."""
+    global _TC_OK
+    if _TC_OK is None:
+        _TC_OK = os.environ.get("ACMB200_TC_READY", "0") == "1"
+    return _TC_OK
+
+
+def default_dtype() -> str:
+    d = os.environ.get("ACMB200_DTYPE", "bf16").lower()
+    if d in ("bf16", "bfloat16"):
+        return "bf16"
+    if d in ("fp32", "f32", "float32"):
+        return "fp32"
+    raise ValueError(f"ACMB200_DTYPE={d!r}: expected bf16 or fp32")
+
+
+def build_pack(fp, f, a_vecs, att_vec, ln_params):
+    """Pack the channel-attention parameters in the layout of include/acm_b200.h."""
+    dev = att_vec.device
+    pack = torch.zeros(12 * fp + 16, dtype=torch.float32, device=dev)
+    for k, a in enumerate(a_vecs):
+        pack[k * fp:k * fp + f] = a.reshape(-1)
+    kk = att_vec.shape[0]
+    pack[4 * fp:4 * fp + 16].view(4, 4)[:kk, :kk] = att_vec
+    if ln_params is not None:
+        for k, (g, b) in enumerate(ln_params):
+            pack[4 * fp + 16 + k * fp:4 * fp + 16 + k * fp + f] = g
+            pack[8 * fp + 16 + k * fp:8 * fp + 16 + k * fp + f] = b
+    return pack
+
+
+def build_wcat(fp, f, ws, dtype):
+    fin = ws[0].shape[0]
+    wcat = torch.zeros(fin, 3 * fp, dtype=torch.float32, device=ws[0].device)
+    for k, w in enumerate(ws):
+        wcat[:, k * fp:k * fp + f] = w
+    return wcat.to(dtype)
+
+
+class AcmLayerFunction(torch.autograd.Function):
+    """Inputs: op, cfg, x, W_low, W_high, W_mlp, a_low, a_high, a_mlp, att_vec, struc_low,
+    a_struc, then (only when LayerNorm is live) gamma_k, beta_k per channel.
+    Outputs: Y [n, F] (differentiable), att [n, K] (non-differentiable)."""
+
+    @staticmethod
+    def forward(ctx, op: AcmOperator, cfg: LayerConfig, x, w_low, w_high, w_mlp, a_low, a_high, a_mlp, att_vec,
+                struc_low, a_struc, *ln_flat):
+        if not x.is_cuda:
+            raise RuntimeError("acm_gnn_b200: CUDA tensors only (there is no CPU fallback)")
+        tdt, cdt = cfg.storage()
+        n, fin = x.shape
+        f = w_low.shape[1]
+        fp = padded_width(f)
+        K = cfg.k_channels
+        dev = x.device
+        st = _stream()
+        if n != op.n:
+            raise ValueError(f"input has {n} rows but the operator has {op.n}")
+
+        a_vecs = [a_low, a_high, a_mlp] + ([a_struc] if K == 4 else [])
+        ln_params = None
+        if cfg.ln_live:
+            ln_params = [(ln_flat[2 * k], ln_flat[2 * k + 1]) for k in range(K)]
+        pack = build_pack(fp, f, a_vecs, att_vec, ln_params)
+        wcat = build_wcat(fp, f, (w_low, w_high, w_mlp), tdt)
+
+        impl = cfg.gemm_impl(fin)
+        # staging copy of the layer input in the storage dtype (row stride padded to 8)
+        if cfg.dtype == "bf16":
+            ldx = (fin + 7) // 8 * 8
+            xs = torch.empty(n, ldx, dtype=tdt, device=dev)
+            xc = x.detach().contiguous()
+            _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, xs.data_ptr(), cdt, ldx, st)
+        else:
+            xs = x.detach().contiguous()
+            ldx = fin
+        wcat_t = None
+        if impl == _lib.GEMM_TCGEN05:
+            wcat_t = torch.zeros(3 * fp, ldx, dtype=tdt, device=dev)
+            wcat_t[:, :fin] = wcat.t()
+
+        h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
+        h_i = torch.empty(n, fp, dtype=tdt, device=dev)
+        _lib.call("acm_gemm_xw_fwd", impl, cdt, xs.data_ptr(), ldx, wcat.data_ptr(), _lib.ptr(wcat_t),
+                  h_lh.data_ptr(), h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
+
+        table = h_lh if cfg.dist is None else cfg.dist.all_gather_rows(h_lh)
+
+        o_s = None
+        if K == 4:
+            if op.raw is None:
+                raise ValueError("structure_info=1 needs adj_low_unnormalized")
+            s_loc = struc_low.detach().contiguous()
+            s_tab = torch.empty(s_loc.shape[0], fp, dtype=tdt, device=dev)
+            _lib.call("acm_cast_pad", s_loc.data_ptr(), s_loc.shape[0], f, f, s_tab.data_ptr(), cdt, fp, st)
+            o_s = torch.empty(n, fp, dtype=tdt, device=dev)
+            _lib.call("acm_spmm_plain", cdt, cdt, fp, n, op.raw.rowptr.data_ptr(), op.raw.col.data_ptr(),
+                      op.raw.val.data_ptr(), s_tab.data_ptr(), o_s.data_ptr(), fp, fp, 1, st)
+            del s_tab
+
+        # grad mode is off inside Function.forward: needs_input_grad is the reliable signal
+        # (all False under torch.no_grad(), e.g. ACM-Geometric's evaluate_acmgcn)
+        need_grad = any(ctx.needs_input_grad)
+        y = torch.empty(n, f, dtype=torch.float32, device=dev)
+        att = torch.empty(n, K, dtype=torch.float32, device=dev)
+        sig = torch.empty(n, K, dtype=torch.float32, device=dev) if need_grad else None
+        o_save = torch.empty(n, 2 * fp, dtype=tdt, device=dev) if need_grad else None
+        _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, op.row0,
+                  op.low.rowptr.data_ptr(), op.low.col.data_ptr(), op.low.val.data_ptr(), 0,
+                  table.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s), pack.data_ptr(),
+                  K, int(cfg.ln_live), int(cfg.variant), float(cfg.out_scale),
+                  y.data_ptr(), f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig), st, tag=fp)
+
+        ctx.mark_non_differentiable(att)
+        if need_grad:
+            ctx.op, ctx.cfg = op, cfg
+            ctx.dims = (n, fin, f, fp, K, ldx, impl)
+            ctx.x_needs_grad = bool(ctx.needs_input_grad[2])
+            ctx.n_ln = len(ln_flat)
+            ctx.struc_rows = 0 if struc_low is None else struc_low.shape[0]
+            # variant 1 needs the relu'd forward table (its positivity is the relu mask)
+            ctx.save_for_backward(xs, wcat, wcat_t, h_i, o_save, att, sig, pack, o_s,
+                                  h_lh if cfg.variant else None)
+        return y, att
+
+    @staticmethod
+    def backward(ctx, g, _g_att):
+        xs, wcat, wcat_t, h_i, o_save, att, sig, pack, o_s, p_tab = ctx.saved_tensors
+        op, cfg = ctx.op, ctx.cfg
+        n, fin, f, fp, K, ldx, impl = ctx.dims
+        tdt, cdt = cfg.storage()
+        dev = g.device
+        st = _stream()
+        g = g.contiguous().to(torch.float32)
+
+        t_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
+        dh_all = torch.empty(n, 3 * fp, dtype=tdt, device=dev)
+        dos_pre = torch.empty(n, fp, dtype=tdt, device=dev) if K == 4 else None
+        dpack = torch.zeros(12 * fp + 16, dtype=torch.float32, device=dev)
+        _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
+                  att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
+                  float(cfg.out_scale), t_lh.data_ptr(), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(), st, tag=fp)
+
+        t_table = t_lh if cfg.dist is None else cfg.dist.all_gather_rows(t_lh)
+        _lib.call("acm_spmm_t_bwd", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
+                  op.low.val_t.data_ptr(), t_table.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(), st, tag=fp)
+        del t_table, t_lh
+
+        dwcat = torch.zeros(fin, 3 * fp, dtype=torch.float32, device=dev)
+        _lib.call("acm_gemm_bwd_dw", impl, cdt, xs.data_ptr(), ldx, dh_all.data_ptr(), dwcat.data_ptr(), n, fin, fp, st, tag=fp)
+        dx = None
+        if ctx.x_needs_grad:
+            dx = torch.empty(n, fin, dtype=torch.float32, device=dev)
+            _lib.call("acm_gemm_bwd_dx", impl, cdt, dh_all.data_ptr(), wcat.data_ptr(), _lib.ptr(wcat_t), ldx,
+                      dx.data_ptr(), fin, n, fin, fp, st, tag=fp)
+
+        d_struc = d_a_struc = None
+        if K == 4:
+            nr = ctx.struc_rows
+            if cfg.dist is not None:
+                raise NotImplementedError("structure channel under a row partition")
+            d_struc = torch.empty(nr, f, dtype=torch.float32, device=dev)
+            _lib.call("acm_spmm_plain", cdt, _lib.ACM_F32, fp, nr, op.raw.rowptr_t.data_ptr(), op.raw.col_t.data_ptr(),
+                      op.raw.val_t.data_ptr(), dos_pre.data_ptr(), d_struc.data_ptr(), f, f, 0, st)
+            d_a_struc = dpack[3 * fp:3 * fp + f].reshape(f, 1).clone()
+
+        if cfg.dist is not None:
+            cfg.dist.all_reduce_(dwcat)
+            cfg.dist.all_reduce_(dpack)
+
+        dw = [dwcat[:, k * fp:k * fp + f].contiguous() for k in range(3)]
+        da = [dpack[k * fp:k * fp + f].reshape(f, 1).clone() for k in range(3)]
+        d_att_vec = dpack[4 * fp:4 * fp + 16].view(4, 4)[:K, :K].clone()
+        d_ln = []
+        for k in range(ctx.n_ln // 2):
+            if cfg.ln_live and k < K:
+                d_ln.append(dpack[4 * fp + 16 + k * fp:4 * fp + 16 + k * fp + f].clone())
+                d_ln.append(dpack[8 * fp + 16 + k * fp:8 * fp + 16 + k * fp + f].clone())
+            else:
+                d_ln += [None, None]
+        return (None, None, dx, dw[0], dw[1], dw[2], da[0], da[1], da[2], d_att_vec, d_struc, d_a_struc, *d_ln)

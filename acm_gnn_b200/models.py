@@ -1,0 +1,48 @@
+"""Layer stack used by bench.py, smoke() and the GPU tests on boxes where the reference
+tree is absent.  It mirrors the reference ``GCN`` (ACM-Pytorch/models/models.py:25-166,
+ACM-Geometric/models.py:23-76) for the three working model types
+(acmgcn | acmgcnp | acmgcnpp): dropout -> [mlpX branch] -> layer 0 -> relu -> dropout ->
+(+ xX) -> layer 1, with the same constructor signature and state_dict keys.  When the
+reference tree IS present, its own unmodified ``models.py`` runs on top of the drop-in
+layer instead (acm_gnn_b200/run.py) -- this file is a convenience, not the boundary.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.nn.parameter import Parameter
+
+from . import layers as _layers_pt
+from . import layers_geometric as _layers_geo
+
+
+class GCN(nn.Module):
+    def __init__(self, nfeat, nhid, nclass, nlayers, nnodes, dropout, model_type, structure_info,
+                 variant=False, init_layers_X=1, flavour="pytorch"):
+        super().__init__()
+        if model_type not in ("acmgcn", "acmgcnp", "acmgcnpp"):
+            raise NotImplementedError(f"model_type {model_type!r}: only acmgcn/acmgcnp/acmgcnpp work upstream")
+        L = _layers_pt if flavour == "pytorch" else _layers_geo
+        if model_type == "acmgcnpp":
+            self.mlpX = L.MLP(nfeat, nhid, nhid, num_layers=init_layers_X, dropout=0)
+        self.gcns, self.mlps = nn.ModuleList(), nn.ModuleList()
+        self.model_type, self.structure_info, self.nlayers, self.nnodes = model_type, structure_info, nlayers, nnodes
+        kw = dict(model_type=model_type, variant=variant, structure_info=structure_info)
+        self.gcns.append(L.GraphConvolution(nfeat, nhid, nnodes, **kw))
+        self.gcns.append(L.GraphConvolution(nhid, nclass, nnodes, output_layer=1, **kw))
+        self.dropout = dropout
+        # quirk Q4: allocated, never initialised, never used (models.py:94-96)
+        self.fea_param = Parameter(torch.zeros(1, 1, device=L.device))
+        self.xX_param = Parameter(torch.zeros(1, 1, device=L.device))
+        if model_type == "acmgcnpp":
+            self.mlpX.reset_parameters()
+
+    def forward(self, x, adj_low, adj_high, adj_low_unnormalized):
+        x = F.dropout(x, self.dropout, training=self.training)
+        xX = None
+        if self.model_type == "acmgcnpp":
+            xX = F.dropout(F.relu(self.mlpX(x, input_tensor=True)), self.dropout, training=self.training)
+        fea1 = self.gcns[0](x, adj_low, adj_high, adj_low_unnormalized)
+        fea1 = F.dropout(F.relu(fea1), self.dropout, training=self.training)
+        if xX is not None:
+            fea1 = fea1 + xX
+        return self.gcns[1](fea1, adj_low, adj_high, adj_low_unnormalized)

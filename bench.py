@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Benchmark of the ACM-GCN train step (fwd + loss + bwd + Adam) in edges/sec.
+
+Metric (BASELINE.json): "ACM-GCN fwd+bwd edges/sec at 1/2/4/8 B200; achieved HBM GB/s vs peak".
+Workload: SURVEY.md 8(d) cfg 5 -- synthetic uniform random graph, N = 10 M nodes,
+E = 200 M directed edges (+ N self loops), Fin = hidden = 256, 16 classes, 2-layer
+``acmgcn``, variant 0, dropout 0, bf16 feature tables / fp32 accumulation.  The whole graph
+fits one B200 (peak ~80 GB), so N=1 runs the full size; with N>1 GPUs the SAME graph is
+1-D row-partitioned (strong scaling, NCCL all-gather of the operand table per aggregation).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+`--impl reference` times the CPU oracle (the reference's torch.sparse.mm COO path restated
+in oracle/acm_oracle.py -- the reference itself is Python and does not travel to the GPU
+box) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "acm_gcn_train_step_edges_per_sec"
+UNIT = "edges/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=10_000_000)
+    ap.add_argument("--edges", type=int, default=200_000_000, help="directed edges of A (before + I)")
+    ap.add_argument("--fin", type=int, default=256)
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--nclass", type=int, default=16)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--gemm", default=os.environ.get("ACMB200_GEMM", "auto"))
+    ap.add_argument("--cpu-nodes", type=int, default=100_000, help="size of the CPU-baseline sample graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------------------
+
+def synthetic_graph_gpu(n, e_directed, device, seed=0):
+    """Uniform random undirected pairs, self loops dropped, symmetrised, duplicates coalesced."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    eu = e_directed // 2
+    src = torch.randint(0, n, (eu,), generator=g, device=device, dtype=torch.int64)
+    dst = torch.randint(0, n, (eu,), generator=g, device=device, dtype=torch.int64)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    key = torch.unique(torch.cat([src * n + dst, dst * n + src]))
+    del src, dst, keep
+    row = torch.div(key, n, rounding_mode="floor")
+    col = key - row * n
+    return row, col
+
+
+class Clocks:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ----------------------------------------------------------------------------------------
+
+def cpu_step_factory(n, e_directed, fin, hidden, nclass):
+    import numpy as np
+    import torch
+    from oracle import acm_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    row, col = O.synthetic_edges(n, e_directed, seed=0)
+    op = O.build_operator(row, col, n, "pytorch")
+    low, high = O.operator_to_torch(op)  # both sparse COO: the torch.sparse.mm path BASELINE.json names
+    g = torch.Generator().manual_seed(1)
+    x = O.row_normalise_features(torch.rand(n, fin, generator=g))
+    labels = torch.randint(0, nclass, (n,), generator=g)
+    idx = torch.randperm(n, generator=g)[: int(0.6 * n)]
+    gp = torch.Generator().manual_seed(42)
+    params = O.init_gcn_params(fin, hidden, nclass, 0, "acmgcn", 0, gp)
+    leaves = [t.requires_grad_(True) for grp in params.values() for k, t in grp.items() if not k.startswith(("layer_norm", "struc", "att_struc"))]
+    opt = torch.optim.Adam(leaves, lr=0.05, weight_decay=1e-3)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        out, _ = O.gcn_forward(params, x, low, high, None)
+        loss = O.train_step_loss(out, labels, idx)
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step, op.nnz
+
+
+def time_cpu(steps, warmup, n, args):
+    e = int(round(args.edges * (n / args.nodes)))
+    step, nnz = cpu_step_factory(n, e, args.fin, args.hidden, args.nclass)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return nnz / dt, dt * 1e3, nnz
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = min(args.cpu_nodes, args.nodes)
+    val, ms, nnz = time_cpu(args.steps, args.warmup, n, args)
+    sample = (f"CPU oracle (torch.sparse.mm COO, fp32) full train step on a scaled graph N={n}, nnz={nnz} "
+              f"(same mean degree and widths as the {args.nodes}-node workload)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"synthetic uniform random graph N={args.nodes} E={args.edges} (+N self loops), Fin={args.fin} "
+                        f"hidden={args.hidden} classes={args.nclass}, 2-layer acmgcn variant 0 dropout 0 (SURVEY 8d cfg 5)",
+            "nodes": args.nodes, "edges": args.edges, "fin": args.fin, "hidden": args.hidden, "nclass": args.nclass,
+            "step": "forward + log_softmax/NLL + backward + Adam.step",
+            "partition": f"1-D row partition over {world} GPU(s), NCCL all-gather of the operand table" if world > 1 else "single GPU",
+            "l2": "inputs >> L2 (no flush)" if args.nodes * args.hidden * 2 > 4 * 126e6 else "L2 flushed between timed steps"}
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    os.environ["ACMB200_DTYPE"] = args.dtype
+    os.environ["ACMB200_GEMM"] = args.gemm
+
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    from acm_gnn_b200 import layers as L
+    L.device = dev
+    from acm_gnn_b200.dist import RowPartition, attach
+
+    n, fin, hid, ncls = args.nodes, args.fin, args.hidden, args.nclass
+    free, total = torch.cuda.mem_get_info()
+    est = (n / world) * (fin * 4 * 2 + hid * 32) + (args.edges / world) * 16 + (n * hid * 4 if world > 1 else 0) + args.edges * 8 * 6
+    if est > 0.92 * free:
+        raise SystemExit(f"workload needs ~{est/1e9:.0f} GB, only {free/1e9:.0f} GB free: refusing to risk an OOM")
+
+    # ---- inputs, resident in HBM before the timed region -------------------------------------
+    row, col = synthetic_graph_gpu(n, args.edges, dev, seed=0)
+    op_full = A.AcmOperator.from_edges(row, col, n, "pytorch")
+    del row, col
+    nnz_global = op_full.nnz
+    part = None
+    if world > 1:
+        part = RowPartition(n)
+        op = op_full.partition(part.r0, part.r1)
+        del op_full
+        r0, r1 = part.r0, part.r1
+    else:
+        op, r0, r1 = op_full, 0, n
+    torch.cuda.empty_cache()
+    n_loc = r1 - r0
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + rank)
+    x = torch.rand(n_loc, fin, generator=g, device=dev)
+    x.div_(x.sum(1, keepdim=True))  # row L1 normalisation as train_prep does (utils.py:612-617)
+    labels = torch.randint(0, ncls, (n_loc,), generator=g, device=dev)
+    idx_train = torch.nonzero(torch.rand(n_loc, generator=g, device=dev) < 0.6).squeeze(1)
+    n_train = torch.tensor([idx_train.numel()], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(n_train)
+    n_train_global = float(n_train.item())
+
+    torch.manual_seed(42)  # identical replicated parameters on every rank
+    model = A.GCN(fin, hid, ncls, 2, n, 0.0, "acmgcn", 0, variant=False).to(dev)
+    if part is not None:
+        attach(model, part)
+    params = [p for k, p in model.named_parameters() if k not in ("fea_param", "xX_param")]
+    opt = torch.optim.Adam(params, lr=0.05, weight_decay=1e-3)  # reference defaults, arg_parser.py:51-53
+
+    def step(xin, lab):
+        model.train()
+        opt.zero_grad(set_to_none=True)
+        out = model(xin, op, None, None)
+        lp = F.log_softmax(out, dim=1)
+        loss = F.nll_loss(lp[idx_train], lab[idx_train], reduction="sum") / n_train_global
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush = None
+    if args.nodes * args.hidden * 2 <= 4 * 126e6:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    for _ in range(args.warmup):
+        step(x, labels)
+    barrier()
+    torch.cuda.reset_peak_memory_stats()
+
+    timer = _lib.KernelTimer()
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _lib.launch_count()
+    spans = []
+    barrier()
+    _lib.set_timer(timer)
+    if flush is None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            loss = step(x, labels)
+        b.record()
+        spans.append((a, b))
+    else:
+        for _ in range(args.steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            loss = step(x, labels)
+            b.record()
+            spans.append((a, b))
+    _lib.set_timer(None)
+    barrier()
+    total_ms = sum(s.elapsed_time(e) for s, e in spans)
+    launches = _lib.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = nnz_global / (ms_per_step * 1e-3)
+    peak_mem = torch.cuda.max_memory_allocated() / 1e9
+    final_loss = float(loss.item())
+
+    # ---- roofline of the dominant kernel: fused SpMM + attention + mix, layer 0 ---------------
+    summ = timer.summary()
+    from acm_gnn_b200.functional import padded_width
+    fp0 = padded_width(hid)
+    s_el = 2 if args.dtype == "bf16" else 4
+    nnz_loc = op.nnz
+    alg_bytes = nnz_loc * (2 * fp0 * s_el + 4) + n_loc * (fp0 * s_el + hid * 4 + 8) + n_loc * (2 * fp0 * s_el + 12)
+    key = f"acm_spmm_mix_fwd:{fp0}"
+    roof = None
+    if key in summ:
+        cnt, ms = summ[key]
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = alg_bytes / (ms / cnt * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{key}:N{args.nodes}:E{args.edges}:{args.dtype}:w{world}")
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": "spmm_mix_fwd_kernel (fused aggregation+attention+mix, layer 0)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650",
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms / cnt, "launches_timed": cnt}
+    breakdown = {k: round(v[1] / args.steps, 4) for k, v in sorted(summ.items())}
+
+    # ---- end to end through the public module API with HOST buffers ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(n_loc, fin, dtype=torch.float32, pin_memory=True)
+        xh.copy_(x)
+        lh = torch.empty(n_loc, dtype=torch.int64, pin_memory=True)
+        lh.copy_(labels)
+        xd, ld = torch.empty_like(x), torch.empty_like(labels)
+        k_e2e = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            xd.copy_(xh, non_blocking=True)
+            ld.copy_(lh, non_blocking=True)
+            return float(step(xd, ld).item())  # .item(): device -> host read of the loss
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / k_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": nnz_global / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(xh.numel() * 4 + lh.numel() * 8), "d2h_bytes_per_step": 4,
+               "ms_per_step": float(dt.item()) * 1e3, "steps": k_e2e,
+               "note": "per-rank pinned host features+labels copied H2D every step, loss read back; operator CSR stays resident (as in the reference, utils.py:383-385)"}
+        del xh, lh, xd, ld
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ncpu = min(args.cpu_nodes, n)
+        v, ms_c, nnz_c = time_cpu(2, 1, ncpu, args)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"CPU oracle (torch.sparse.mm COO path, fp32) train step on scaled graph N={ncpu}, nnz={nnz_c}, same mean degree/widths; 1 warm-up + 2 timed steps, {ms_c:.0f} ms/step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches,
+            "nnz": nnz_global, "peak_mem_gb": round(peak_mem, 2), "loss": final_loss,
+            "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

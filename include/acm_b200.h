@@ -1,0 +1,148 @@
+/*
+ * acm_b200.h  --  C ABI of libacm_b200.so, the B200 (sm_100a) kernels behind the ACM
+ * graph-convolution layer of SitaoLuan/ACM-GNN.
+ *
+ * The reference has no FFI: its "plugin API" is the Python class
+ * `GraphConvolution` (ACM-Pytorch/models/layers.py:14-242, ACM-Geometric/layers.py:13-120)
+ * whose forward is a chain of torch ops.  Each entry point below replaces one group of
+ * those torch calls; the reference line(s) it stands in for are cited per function.  The
+ * binding a maintainer adds on the reference side is a ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into memory owned by the caller (torch caching
+ *     allocator); the library never allocates, frees or retains device memory;
+ *   - `stream` is a cudaStream_t; every call is asynchronous on it, no internal
+ *     device synchronisation;
+ *   - return value 0 = success, otherwise a cudaError_t or ACM_ERR_* code and
+ *     acm_last_error_string() describes it (thread local); nothing throws or aborts;
+ *   - storage dtype `T` of feature tables: ACM_F32 or ACM_BF16; accumulation is fp32;
+ *   - `fp` is the feature width padded to one of {8,16,32,64,128,256}; `f` <= fp the true
+ *     width (out_features).  Padding columns are zero.
+ */
+#ifndef ACM_B200_H_
+#define ACM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACM_F32 0
+#define ACM_BF16 1
+
+#define ACM_ERR_BAD_ARG 10001
+#define ACM_ERR_UNSUPPORTED 10002
+
+/* GEMM implementation selector */
+#define ACM_GEMM_SIMT 0   /* CUDA-core fp32-FMA tiles: exact-fp32 parity mode, any shape */
+#define ACM_GEMM_TCGEN05 1 /* tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM), TMA fed */
+
+/* Channel-attention parameter pack (fp32, device), identical layout for values and for
+ * gradients.  Channel order: 0 low, 1 high, 2 identity(mlp), 3 structure.
+ *   [0          , 4*fp)      a_vec[k][fp]   att_vec_low/high/mlp, att_struc_low  (layers.py:45-62)
+ *   [4*fp       , 4*fp+16)   att_vec[j][k]  row-major 4x4 slots, KxK used        (layers.py:64-67)
+ *   [4*fp+16    , 8*fp+16)   ln_gamma[k][fp]  layer_norm_*.weight                (layers.py:52-59)
+ *   [8*fp+16    , 12*fp+16)  ln_beta[k][fp]   layer_norm_*.bias
+ */
+#define ACM_PACK_FLOATS(fp) (12 * (fp) + 16)
+
+int acm_version(void);
+const char* acm_last_error_string(void);
+/* number of kernel launches issued by this library in this process (for bench.py's
+ * gpu_launches claim) */
+int64_t acm_launch_count(void);
+
+/* ---- operator construction --------------------------------------------------------
+ * Replaces the adjacency preprocessing the reference does with dense torch / scipy:
+ * ACM-Pytorch/utils.py:421-438,626-628 (normalize_tensor(eye + A.to_dense())) and
+ * ACM-Geometric/utils.py:5-19, train.py:76-80. */
+
+/* rowptr[int64, n+1] from the row ids of a row-major-sorted (coalesced) COO. */
+int acm_csr_rowptr(const int64_t* row_sorted, int64_t nnz, int64_t n, int64_t* rowptr, void* stream);
+
+/* Degree normalisation of M = A + I given CSR multiplicities mult[nnz] (fp32):
+ * rowsum_i = sum_j m_ij ; rinv_i = 1/rowsum_i (inf -> 0) ; w_ij = fl32(rinv_i * m_ij).
+ * Bit-exact with torch.pow(rowsum,-1) / torch.mm(diag(r_inv), mx) on fp32. */
+int acm_degree_normalise(const int64_t* rowptr, const float* mult, int64_t n,
+                         float* rowsum, float* rinv, float* w, void* stream);
+
+/* Values of the transposed operator on a SYMMETRIC sparsity pattern: for every stored
+ * (i,j) writes w_t[pos(j,i)] = w[pos(i,j)].  *not_symmetric (device int, zeroed by the
+ * caller) is set to 1 if some (j,i) is missing, in which case the caller must build an
+ * explicit transpose. */
+int acm_csr_transpose_values(const int64_t* rowptr, const int32_t* col, const float* w, int64_t n,
+                             float* w_t, int* not_symmetric, void* stream);
+
+/* fp32 [rows, cols] (row stride ld_src) -> T [rows, ld_dst], zero-filling columns
+ * cols..ld_dst-1.  The bf16 staging copy of the layer input. */
+int acm_cast_pad(const float* src, int64_t rows, int64_t cols, int64_t ld_src,
+                 void* dst, int dst_dtype, int64_t ld_dst, void* stream);
+
+/* ---- dense feature transforms -------------------------------------------------------
+ * X [n, fin] (row stride ldx), Wcat = [W_low | W_high | W_mlp] zero-padded to
+ * [fin(ldw rows used: fin), 3*fp]; WcatT its transpose [3*fp, ldx]. */
+
+/* layers.py:163-165,179-194: HL,HH,HI = mm(X, weight_{low,high,mlp}) in ONE pass over X.
+ * Writes h_lh [n, 2*fp] = [HL | HH] (the gather table) and h_i [n, fp].  relu_lh != 0
+ * applies relu to the [HL|HH] part (variant=True, layers.py:178-184). */
+int acm_gemm_xw_fwd(int impl, int dtype, const void* x, int64_t ldx, const void* wcat, const void* wcat_t,
+                    void* h_lh, void* h_i, int64_t n, int64_t fin, int64_t fp, int relu_lh, void* stream);
+
+/* autograd of the three torch.mm: dWcat[fin, 3*fp] (fp32, zeroed by caller; accumulated
+ * atomically over split-K slices) = X^T . dH,  dH [n, 3*fp] = [dHL | dHH | dHI]. */
+int acm_gemm_bwd_dw(int impl, int dtype, const void* x, int64_t ldx, const void* dh,
+                    float* dwcat, int64_t n, int64_t fin, int64_t fp, void* stream);
+
+/* dX [n, fin] (fp32, row stride lddx) = dH . Wcat^T. */
+int acm_gemm_bwd_dx(int impl, int dtype, const void* dh, const void* wcat, const void* wcat_t, int64_t ldwt,
+                    float* dx, int64_t lddx, int64_t n, int64_t fin, int64_t fp, void* stream);
+
+/* ---- fused aggregation + channel attention + mix (THE hot kernel) -------------------
+ * layers.py:176-204 + attention3/attention4 (94-152) in one launch:
+ *   acc  = sum_j val_ij * table[col_ij]            (one gather of the [HL|HH] row per edge)
+ *   S_L  = rowscale_i*acc_L ; S_H = table_H[i] - rowscale_i*acc_H     (A_high = I - A_low)
+ *   variant 0: O_L,O_H = relu(S_L),relu(S_H) ; variant 1 (table already relu'd): O = S
+ *   O_I = relu(h_i) ; optional 4th channel O_S given (already relu'd)
+ *   z_k = [LayerNorm_k](O_k).a_k ; s = sigmoid(z) ; att = softmax(s.att_vec/K)
+ *   Y   = out_scale * sum_k att_k O_k
+ * Rows: this call computes rows [0,n_rows) whose global ids are row0+r; `table` is the
+ * full (all-gathered) table indexed by global column ids.  val/rowscale may be NULL (=1).
+ * o_save/sig may be NULL (inference). */
+int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
+                     const int64_t* rowptr, const int32_t* col, const float* val, const float* rowscale,
+                     const void* table, const void* h_i, const void* o_s,
+                     const float* pack, int k_channels, int ln_live, int variant, float out_scale,
+                     float* y, int64_t ldy, void* o_save, float* att, float* sig, void* stream);
+
+/* Row-local backward of the attention/mix/relu part (autograd of layers.py:94-152,
+ * 185-204).  g = dL/dY [n_rows, f].  Writes t_lh [n_rows, 2*fp] = [dS_L | dS_H] (the table
+ * the transposed aggregation gathers), dh_all[:, 2fp:3fp] = dHI, optional dos_pre (grad
+ * of the structure channel before its relu) and atomically accumulates the parameter
+ * gradients into dpack (same layout as pack; zeroed by caller). */
+int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
+                const float* g, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
+                const float* att, const float* sig, const float* pack,
+                int k_channels, int ln_live, int variant, float out_scale,
+                void* t_lh, void* dh_all, void* dos_pre, float* dpack, void* stream);
+
+/* Transposed aggregation (autograd of torch.spmm(adj_low,.) / torch.spmm(adj_high,.)):
+ *   dHL = A_low^T dS_L ; dHH = dS_H - A_low^T dS_H     -> dh_all[:, 0:2fp]
+ * (rowptr_t,col_t,val_t) is the CSR of A_low^T (same arrays as A_low when the pattern is
+ * symmetric, with acm_csr_transpose_values).  variant 1: p_table = the relu'd forward
+ * table; the result is masked by p > 0 (relu before aggregation). */
+int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
+                   const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
+                   const void* t_table, const void* p_table, void* dh_all, void* stream);
+
+/* Plain single-table aggregation out = [relu](A . table), table T [*, fp]; used for the
+ * structure channel relu(mm(adj_low_unnormalized, struc_low)) (layers.py:207-209) and its
+ * transpose.  out dtype out_dtype, row stride ld_out, f_out valid columns. */
+int acm_spmm_plain(int dtype, int out_dtype, int fp, int64_t n_rows,
+                   const int64_t* rowptr, const int32_t* col, const float* val,
+                   const void* table, void* out, int64_t ld_out, int f_out, int relu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACM_B200_H_ */

@@ -1,0 +1,244 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via the drop-in module) against
+(1) the golden vectors produced by the unmodified reference and (2) the CPU oracle on
+seeded inputs.  Run on the B200 box:  python -m pytest tests -m gpu -x -q
+
+Stated tolerances (north_star: "within a stated fp32 tolerance"):
+  fp32 storage mode : max|err| <= 2e-5 * max|ref| + elementwise rtol 2e-4 (+atol 2e-5)
+                      -- fp32 everywhere, only the summation order differs from ATen;
+  bf16 storage mode : max|err| <= 3e-2 * max|ref|  (feature tables, saved activations and
+                      the GEMM operands are bf16 = 8 mantissa bits; accumulation fp32).
+  CSR indices / degree normalisation: bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, Golden, O, golden_cases
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": dict(norm=2e-5, rtol=2e-4, atol=2e-5), "bf16": dict(norm=3e-2, rtol=None, atol=None)}
+
+
+def _close(got, ref, mode, what):
+    got = got.detach().float().cpu().numpy() if torch.is_tensor(got) else np.asarray(got)
+    ref = ref.detach().float().cpu().numpy() if torch.is_tensor(ref) else np.asarray(ref)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    assert np.isfinite(got).all(), what
+    t = TOL[mode]
+    scale = max(float(np.abs(ref).max()), 1e-12)
+    err = float(np.abs(got - ref).max())
+    assert err <= t["norm"] * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e} ({mode})"
+    if t["rtol"] is not None:
+        np.testing.assert_allclose(got, ref, rtol=t["rtol"], atol=max(t["atol"], t["norm"] * scale), err_msg=what)
+
+
+def _cuda_model(g: Golden, mode):
+    import acm_gnn_b200 as A
+    os.environ["ACMB200_DTYPE"] = mode
+    model = A.GCN(g.nfeat, g.nhid, g.nclass, 2, g.n, 0.0, g.model_type, g.structure_info,
+                  variant=bool(g.variant), flavour=g.flavour).cuda()
+    sd = {k[len("param/"):]: torch.from_numpy(g.z[k]) for k in g.z.files if k.startswith("param/")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    return model
+
+
+def _run_cuda(g: Golden, mode):
+    model = _cuda_model(g, mode)
+    low, high, un = g.adjacency()
+    low, high = low.cuda(), high.cuda()
+    un = un.cuda() if un is not None else None
+    x = g.x.clone().cuda().requires_grad_(True)
+    model.train()
+    out = model(x, low, high, un)
+    loss = torch.nn.functional.nll_loss(torch.log_softmax(out, 1)[g.idx_train.cuda()], g.labels.cuda()[g.idx_train.cuda()])
+    loss.backward()
+    torch.cuda.synchronize()
+    return model, out, loss, x.grad
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", golden_cases())
+def test_gcn_matches_reference_golden(name, mode):
+    """Forward output, attention columns, loss and EVERY gradient of a 2-layer model against
+    the stored run of the reference's own GCN (tests/golden/make_golden.py)."""
+    g = Golden(name)
+    model, out, loss, gx = _run_cuda(g, mode)
+    z = g.z
+    _close(out, z["out"], mode, "out")
+    _close(loss, z["loss"], mode, "loss")
+    for li, layer in enumerate(model.gcns):
+        cols = [layer.att_low, layer.att_high, layer.att_mlp]
+        if g.structure_info and g.model_type != "acmgcn":
+            cols.append(layer.att_struc_vec_low)
+        _close(torch.cat(cols, 1), z[f"att{li}"], mode, f"att{li}")
+    _close(gx, z["grad_x"], mode, "grad_x")
+    ref_grads = g.grads()
+    n_checked = 0
+    for k, p in model.named_parameters():
+        if k in ("fea_param", "xX_param") or ".bns." in k:
+            continue
+        rg = ref_grads[k]
+        if rg.size == 0:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        assert p.grad is not None, k
+        _close(p.grad, rg, mode, "grad " + k)
+        n_checked += 1
+    assert n_checked >= 14
+
+
+@pytest.mark.parametrize("flavour", ["pytorch", "geometric"])
+def test_operator_from_edges_bit_exact(flavour):
+    """GPU operator construction (CSR indices, 1/deg, weights) is bit-exact with the oracle,
+    which is itself bit-exact with the reference (tests/test_oracle_golden.py)."""
+    import acm_gnn_b200 as A
+    g = Golden("gcn_pt_acmgcn_v0")
+    op_ref = O.build_operator(g.row, g.col, g.n, flavour)
+    op = A.AcmOperator.from_edges(torch.from_numpy(g.row).cuda(), torch.from_numpy(g.col).cuda(), g.n, flavour)
+    assert np.array_equal(op.low.rowptr.cpu().numpy(), op_ref.rowptr)
+    assert np.array_equal(op.low.col.cpu().numpy().astype(np.int64), op_ref.col)
+    assert np.array_equal(op.low.val.cpu().numpy().view(np.uint32), op_ref.w_low.view(np.uint32))
+    assert np.array_equal(op.rinv.cpu().numpy().view(np.uint32), op_ref.rinv.view(np.uint32))
+    hi = op.high_to_torch_coo()
+    keep = op_ref.w_high != 0
+    assert np.array_equal(hi.values().cpu().numpy().view(np.uint32), op_ref.w_high[keep].view(np.uint32))
+    # transpose values: w_t[pos(j,i)] == w[pos(i,j)]
+    dense = op.to_torch_coo().to_dense().cpu()
+    rows = op.low.rows().cpu()
+    cols = op.low.col.cpu().long()
+    assert op.low.symmetric_pattern
+    assert torch.equal(op.low.val_t.cpu(), dense[cols, rows])
+
+
+@pytest.mark.parametrize("ds", ["cora", "squirrel"])
+def test_dataset_operator_bit_exact(ds):
+    """BASELINE configs 1-2 fixture graphs: CSR + values from the edge list on the GPU equal
+    the operator the reference's train_prep recipe builds (golden)."""
+    import acm_gnn_b200 as A
+    z = np.load(os.path.join(GOLDEN, f"dataset_{ds}.npz"))
+    n = int(z["n"])
+    op = A.AcmOperator.from_edges(torch.from_numpy(z["row"].astype(np.int64)).cuda(),
+                                  torch.from_numpy(z["col"].astype(np.int64)).cuda(), n, "pytorch",
+                                  edge_val=torch.from_numpy(z["raw_val"]).cuda())
+    assert np.array_equal(op.low.rowptr.cpu().numpy(), z["low_crow"].astype(np.int64))
+    assert np.array_equal(op.low.col.cpu().numpy(), z["low_col"])
+    assert np.array_equal(op.low.val.cpu().numpy().view(np.uint32), z["low_val"].view(np.uint32))
+
+
+def test_from_adjacency_dense_and_coo_agree():
+    import acm_gnn_b200 as A
+    g = Golden("gcn_pt_acmgcn_v0")
+    op_ref = g.operator()
+    low_d, high = O.operator_to_torch(op_ref, dense_low=True)
+    low_s, _ = O.operator_to_torch(op_ref, dense_low=False)
+    a = A.AcmOperator.from_adjacency(low_d.cuda(), high.cuda())
+    b = A.AcmOperator.from_adjacency(low_s.cuda(), high.cuda())
+    for x, y in ((a.low.rowptr, b.low.rowptr), (a.low.col, b.low.col), (a.low.val, b.low.val), (a.low.val_t, b.low.val_t)):
+        assert torch.equal(x, y)
+    assert np.array_equal(a.low.val.cpu().numpy().view(np.uint32), op_ref.w_low.view(np.uint32))
+    with pytest.raises(ValueError):
+        A.AcmOperator.from_adjacency(low_s.cuda(), (2.0 * high).cuda())
+
+
+def _oracle_layer(p, x, op_ref, variant, un=None, model_type="acmgcn", structure_info=0, flavour="pytorch"):
+    low, high = O.operator_to_torch(op_ref)
+    return O.layer_forward(p, x, low, high, un, model_type=model_type, variant=variant,
+                           structure_info=structure_info, flavour=flavour)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("f", [2, 7, 16, 24, 64, 100, 256])
+@pytest.mark.parametrize("variant", [False, True])
+def test_layer_vs_oracle_widths(f, variant, mode):
+    """Single layer forward+backward against the oracle for every padded width class
+    (8..256), on a graph with empty-neighbourhood rows, data self-loops and a hub node."""
+    import acm_gnn_b200 as A
+    torch.manual_seed(f * 2 + int(variant))
+    n, fin = 333, 20
+    row, col = O.synthetic_edges(n - 3, 2400, seed=f, zipf=0.8)  # last 3 nodes isolated
+    hub = np.arange(1, 200)
+    row = np.concatenate([row, np.zeros_like(hub), hub, [5, 9]])
+    col = np.concatenate([col, hub, np.zeros_like(hub), [5, 9]])
+    op_ref = O.build_operator(row, col, n)
+    os.environ["ACMB200_DTYPE"] = mode
+    layer = A.GraphConvolution(fin, f, n, "acmgcn", variant=variant).cuda()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    x = torch.randn(n, fin)
+    xc = x.clone().cuda().requires_grad_(True)
+    xo = x.clone().requires_grad_(True)
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    y = layer(xc, op, None, None)
+    yo, atto = _oracle_layer(p, xo, op_ref, variant)
+    w = torch.randn(n, f)
+    (y * w.cuda()).sum().backward()
+    (yo * w).sum().backward()
+    _close(y, yo, mode, "y")
+    _close(torch.cat([layer.att_low, layer.att_high, layer.att_mlp], 1), atto, mode, "att")
+    _close(xc.grad, xo.grad, mode, "dx")
+    for k in ("weight_low", "weight_high", "weight_mlp", "att_vec_low", "att_vec_high", "att_vec_mlp", "att_vec"):
+        _close(getattr(layer, k).grad, p[k].grad, mode, "d" + k)
+
+
+def test_directed_graph_explicit_transpose():
+    """--directed (ACM-Geometric/parse.py:42): non-symmetric pattern -> explicit CSR of A^T."""
+    import acm_gnn_b200 as A
+    os.environ["ACMB200_DTYPE"] = "fp32"
+    rng = np.random.default_rng(3)
+    n, fin, f = 120, 9, 16
+    row, col = rng.integers(0, n, 700), rng.integers(0, n, 700)
+    op_ref = O.build_operator(row, col, n, "geometric")
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n, "geometric")
+    assert op.low.symmetric_pattern is False
+    layer = A.GraphConvolution(fin, f, n, "acmgcn", variant=True).cuda()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    x = torch.randn(n, fin)
+    xc, xo = x.clone().cuda().requires_grad_(True), x.clone().requires_grad_(True)
+    y = layer(xc, op, None, None)
+    yo, _ = _oracle_layer(p, xo, op_ref, True)
+    y.square().sum().backward()
+    yo.square().sum().backward()
+    _close(y, yo, "fp32", "y")
+    _close(xc.grad, xo.grad, "fp32", "dx")
+    _close(layer.weight_low.grad, p["weight_low"].grad, "fp32", "dWl")
+    _close(layer.weight_high.grad, p["weight_high"].grad, "fp32", "dWh")
+
+
+def test_no_grad_and_eval_forward():
+    """Inference path (Geometric evaluates under torch.no_grad, data_utils.py:153): nothing is
+    saved, output identical to the training forward."""
+    import acm_gnn_b200 as A
+    os.environ["ACMB200_DTYPE"] = "fp32"
+    g = Golden("gcn_geo_acmgcnp_v1")
+    model = _cuda_model(g, "fp32")
+    low, high, un = g.adjacency()
+    x = g.x.cuda()
+    model.eval()
+    with torch.no_grad():
+        o1 = model(x, low.cuda(), high.cuda(), None)
+    o2 = model(x, low.cuda(), high.cuda(), None)
+    assert torch.equal(o1, o2)
+    _close(o1, g.z["out"], "fp32", "out")
+
+
+def test_empty_and_degenerate_inputs():
+    import acm_gnn_b200 as A
+    os.environ["ACMB200_DTYPE"] = "bf16"
+    # graph with no edges at all: A_low = I, high-pass channel is exactly zero
+    n, fin, f = 17, 5, 8
+    e = torch.zeros(0, dtype=torch.int64).cuda()
+    op = A.AcmOperator.from_edges(e, e, n)
+    assert op.nnz == n
+    layer = A.GraphConvolution(fin, f, n, "acmgcn").cuda()
+    x = torch.rand(n, fin).cuda()
+    y = layer(x, op, None, None)
+    assert torch.isfinite(y).all()
+    xb = x.to(torch.bfloat16).float()
+    hl = torch.relu(xb @ layer.weight_low.to(torch.bfloat16).float()).to(torch.bfloat16).float()
+    assert float(layer.att_low.sum() + layer.att_high.sum() + layer.att_mlp.sum()) == pytest.approx(n, rel=1e-5)
+    # wrong device / missing library behaviour: CPU tensors are rejected loudly
+    with pytest.raises(RuntimeError):
+        layer(x.cpu(), op, None, None)
