@@ -20,6 +20,12 @@ from helpers import GOLDEN, Golden, O, golden_cases
 pytestmark = pytest.mark.gpu
 
 TOL = {"fp32": dict(norm=2e-5, rtol=2e-4, atol=2e-5), "bf16": dict(norm=3e-2, rtol=None, atol=None)}
+# Gradients in bf16 storage mode: the saved activations / gradient tables are bf16 and the
+# parameter gradients are heavily cancelling sums, so the element-wise max error is dominated
+# by rounding noise (a CPU emulation of the same bf16 storage points on the fp32 oracle gives
+# 3-15 % of max|ref| -- see DESIGN.md "bf16 mode").  Stated gradient tolerance for bf16:
+# relative Frobenius error <= 0.12 and cosine similarity >= 0.99.
+BF16_GRAD = dict(fro=0.12, cos=0.99)
 
 
 def _close(got, ref, mode, what):
@@ -33,6 +39,21 @@ def _close(got, ref, mode, what):
     assert err <= t["norm"] * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e} ({mode})"
     if t["rtol"] is not None:
         np.testing.assert_allclose(got, ref, rtol=t["rtol"], atol=max(t["atol"], t["norm"] * scale), err_msg=what)
+
+
+def _close_grad(got, ref, mode, what):
+    if mode == "fp32":
+        return _close(got, ref, mode, what)
+    got = got.detach().double().cpu().numpy().ravel() if torch.is_tensor(got) else np.asarray(got, np.float64).ravel()
+    ref = ref.detach().double().cpu().numpy().ravel() if torch.is_tensor(ref) else np.asarray(ref, np.float64).ravel()
+    assert got.shape == ref.shape and np.isfinite(got).all(), what
+    nr = np.linalg.norm(ref)
+    if nr < 1e-12:
+        assert np.linalg.norm(got) < 1e-6, what
+        return
+    fro = np.linalg.norm(got - ref) / nr
+    cos = float(got @ ref) / (np.linalg.norm(got) * nr + 1e-300)
+    assert fro <= BF16_GRAD["fro"] and cos >= BF16_GRAD["cos"], f"{what}: rel.fro {fro:.3e} cos {cos:.5f} (bf16)"
 
 
 def _cuda_model(g: Golden, mode):
@@ -75,7 +96,7 @@ def test_gcn_matches_reference_golden(name, mode):
         if g.structure_info and g.model_type != "acmgcn":
             cols.append(layer.att_struc_vec_low)
         _close(torch.cat(cols, 1), z[f"att{li}"], mode, f"att{li}")
-    _close(gx, z["grad_x"], mode, "grad_x")
+    _close_grad(gx, z["grad_x"], mode, "grad_x")
     ref_grads = g.grads()
     n_checked = 0
     for k, p in model.named_parameters():
@@ -86,7 +107,7 @@ def test_gcn_matches_reference_golden(name, mode):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
             continue
         assert p.grad is not None, k
-        _close(p.grad, rg, mode, "grad " + k)
+        _close_grad(p.grad, rg, mode, "grad " + k)
         n_checked += 1
     assert n_checked >= 14
 
@@ -178,9 +199,9 @@ def test_layer_vs_oracle_widths(f, variant, mode):
     (yo * w).sum().backward()
     _close(y, yo, mode, "y")
     _close(torch.cat([layer.att_low, layer.att_high, layer.att_mlp], 1), atto, mode, "att")
-    _close(xc.grad, xo.grad, mode, "dx")
+    _close_grad(xc.grad, xo.grad, mode, "dx")
     for k in ("weight_low", "weight_high", "weight_mlp", "att_vec_low", "att_vec_high", "att_vec_mlp", "att_vec"):
-        _close(getattr(layer, k).grad, p[k].grad, mode, "d" + k)
+        _close_grad(getattr(layer, k).grad, p[k].grad, mode, "d" + k)
 
 
 def test_directed_graph_explicit_transpose():
@@ -236,8 +257,6 @@ def test_empty_and_degenerate_inputs():
     x = torch.rand(n, fin).cuda()
     y = layer(x, op, None, None)
     assert torch.isfinite(y).all()
-    xb = x.to(torch.bfloat16).float()
-    hl = torch.relu(xb @ layer.weight_low.to(torch.bfloat16).float()).to(torch.bfloat16).float()
     assert float(layer.att_low.sum() + layer.att_high.sum() + layer.att_mlp.sum()) == pytest.approx(n, rel=1e-5)
     # wrong device / missing library behaviour: CPU tensors are rejected loudly
     with pytest.raises(RuntimeError):
