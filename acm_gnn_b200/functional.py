@@ -58,15 +58,10 @@ class LayerConfig:
         return _lib.GEMM_TCGEN05 if g == "tcgen05" else _lib.GEMM_SIMT
 
 
-_TC_OK = None
-
-
 def tc_available() -> bool:
-    """Whether the tcgen05 GEMM kernels are compiled into the library (probe once)."""
-    global _TC_OK
-    if _TC_OK is None:
-        _TC_OK = os.environ.get("ACMB200_TC_READY", "0") == "1"
-    return _TC_OK
+    """The tcgen05 GEMM kernels (gemm_tc.cu) are the default for bf16 storage; set
+    ACMB200_GEMM=simt to force the CUDA-core path."""
+    return True
 
 
 def default_dtype() -> str:
