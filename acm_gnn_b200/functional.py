@@ -238,3 +238,40 @@ class AcmLayerFunction(torch.autograd.Function):
             else:
                 d_ln += [None, None]
         return (None, None, dx, dw[0], dw[1], dw[2], da[0], da[1], da[2], d_att_vec, d_struc, d_a_struc, *d_ln)
+
+
+class MaskedNllLogSoftmax(torch.autograd.Function):
+    """``F.nll_loss(F.log_softmax(out, 1)[train], labels[train])`` (ACM-Pytorch/utils.py:567-568)
+    as one launch producing the loss and d loss / d out together (acm_nll_log_softmax)."""
+
+    @staticmethod
+    def forward(ctx, out, labels, mask, scale):
+        if not out.is_cuda:
+            raise RuntimeError("acm_gnn_b200: CUDA tensors only (there is no CPU fallback)")
+        out_c = out.detach().contiguous()
+        n, c = out_c.shape
+        loss = torch.zeros((), dtype=torch.float32, device=out.device)
+        need = ctx.needs_input_grad[0]
+        d = torch.empty_like(out_c) if need else None
+        _lib.call("acm_nll_log_softmax", out_c.data_ptr(), c, n, c, labels.data_ptr(), _lib.ptr(mask), float(scale),
+                  loss.data_ptr(), _lib.ptr(d), c, _stream())
+        if need:
+            ctx.save_for_backward(d)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return d * g, None, None, None
+
+
+def nll_log_softmax(out, labels, train_mask=None, n_train=None):
+    """Mean NLL of log_softmax(out) over the rows selected by ``train_mask`` (uint8/bool [N]).
+    ``n_train`` overrides the normaliser (global count under a row partition)."""
+    if labels.dtype != torch.int64:
+        labels = labels.to(torch.int64)
+    if train_mask is not None and train_mask.dtype != torch.uint8:
+        train_mask = train_mask.to(torch.uint8)
+    if n_train is None:
+        n_train = int(train_mask.sum().item()) if train_mask is not None else out.shape[0]
+    return MaskedNllLogSoftmax.apply(out, labels.contiguous(), train_mask, 1.0 / float(n_train))

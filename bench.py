@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--cpu-nodes", type=int, default=100_000, help="size of the CPU-baseline sample graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--torch-loss", action="store_true",
+                    help="use the reference's torch glue (log_softmax + index + nll_loss) instead of the fused loss kernel")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0 = leave default)")
     return ap.parse_args()
 
 
@@ -184,7 +187,7 @@ def workload_config(args, world):
     return {"workload": f"synthetic uniform random graph N={args.nodes} E={args.edges} (+N self loops), Fin={args.fin} "
                         f"hidden={args.hidden} classes={args.nclass}, 2-layer acmgcn variant 0 dropout 0 (SURVEY 8d cfg 5)",
             "nodes": args.nodes, "edges": args.edges, "fin": args.fin, "hidden": args.hidden, "nclass": args.nclass,
-            "step": "forward + log_softmax/NLL + backward + Adam.step",
+            "step": "forward + log_softmax/NLL (" + ("torch glue" if args.torch_loss else "fused acm_nll_log_softmax") + ") + backward + Adam.step",
             "partition": f"1-D row partition over {world} GPU(s), NCCL all-gather of the operand table" if world > 1 else "single GPU",
             "l2": "inputs >> L2 (no flush)" if args.nodes * args.hidden * 2 > 4 * 126e6 else "L2 flushed between timed steps"}
 
@@ -214,6 +217,9 @@ def run_ours(args):
     from acm_gnn_b200 import layers as L
     L.device = dev
     from acm_gnn_b200.dist import RowPartition, attach
+    from acm_gnn_b200.functional import nll_log_softmax
+    if args.l2_fetch:
+        _lib.call("acm_set_l2_fetch_granularity", args.l2_fetch)
 
     n, fin, hid, ncls = args.nodes, args.fin, args.hidden, args.nclass
     free, total = torch.cuda.mem_get_info()
@@ -241,7 +247,8 @@ def run_ours(args):
     x = torch.rand(n_loc, fin, generator=g, device=dev)
     x.div_(x.sum(1, keepdim=True))  # row L1 normalisation as train_prep does (utils.py:612-617)
     labels = torch.randint(0, ncls, (n_loc,), generator=g, device=dev)
-    idx_train = torch.nonzero(torch.rand(n_loc, generator=g, device=dev) < 0.6).squeeze(1)
+    train_mask = (torch.rand(n_loc, generator=g, device=dev) < 0.6).to(torch.uint8)
+    idx_train = torch.nonzero(train_mask).squeeze(1)
     n_train = torch.tensor([idx_train.numel()], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(n_train)
@@ -258,8 +265,11 @@ def run_ours(args):
         model.train()
         opt.zero_grad(set_to_none=True)
         out = model(xin, op, None, None)
-        lp = F.log_softmax(out, dim=1)
-        loss = F.nll_loss(lp[idx_train], lab[idx_train], reduction="sum") / n_train_global
+        if args.torch_loss:  # the reference's glue, utils.py:567-568
+            lp = F.log_softmax(out, dim=1)
+            loss = F.nll_loss(lp[idx_train], lab[idx_train], reduction="sum") / n_train_global
+        else:                # same math, one fused launch (value + gradient)
+            loss = nll_log_softmax(out, lab, train_mask, n_train=n_train_global)
         loss.backward()
         opt.step()
         return loss
@@ -389,7 +399,7 @@ def run_ours(args):
             "config": workload_config(args, world),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches,
             "nnz": nnz_global, "peak_mem_gb": round(peak_mem, 2), "loss": final_loss,
-            "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm,
+            "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

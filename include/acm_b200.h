@@ -142,6 +142,20 @@ int acm_spmm_plain(int dtype, int out_dtype, int fp, int64_t n_rows,
                    const int64_t* rowptr, const int32_t* col, const float* val,
                    const void* table, void* out, int64_t ld_out, int f_out, int relu, void* stream);
 
+/* ---- loss glue of the train step ----------------------------------------
+ * Fused F.log_softmax + NLLLoss on the training rows (ACM-Pytorch/utils.py:567-568,
+ * ACM-Geometric/train.py:133-134), value and gradient in one pass:
+ *   *loss_sum += scale * sum_{mask_i} (logsumexp(x_i) - x_i[label_i])     (zeroed by caller)
+ *   dlogits_i  = scale * (softmax(x_i) - onehot(label_i)) on masked rows, 0 elsewhere (may be NULL)
+ * mask: uint8 per row (NULL = every row); scale = 1/|train| for the reference's mean reduction. */
+int acm_nll_log_softmax(const float* logits, int64_t ld, int64_t n_rows, int n_classes,
+                        const int64_t* labels, const uint8_t* mask, float scale,
+                        float* loss_sum, float* dlogits, int64_t ld_d, void* stream);
+
+/* cudaLimitMaxL2FetchGranularity (32/64/128 bytes) of the current device: narrow rows
+ * (out_features <= 16 -> 64-byte table rows) over-fetch at the default granularity. */
+int acm_set_l2_fetch_granularity(int bytes);
+
 #ifdef __cplusplus
 }
 #endif

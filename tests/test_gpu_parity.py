@@ -266,3 +266,27 @@ def test_empty_and_degenerate_inputs():
     # wrong device / missing library behaviour: CPU tensors are rejected loudly
     with pytest.raises(RuntimeError):
         layer(x.cpu(), op, None, None)
+
+
+@pytest.mark.parametrize("c", [2, 5, 16, 40])
+def test_fused_nll_log_softmax_matches_torch(c):
+    """acm_nll_log_softmax == F.nll_loss(F.log_softmax(out,1)[idx], labels[idx]) (utils.py:567-568),
+    value and gradient."""
+    from acm_gnn_b200.functional import nll_log_softmax
+    torch.manual_seed(c)
+    n = 1003
+    out = (3 * torch.randn(n, c)).cuda().requires_grad_(True)
+    out2 = out.detach().clone().requires_grad_(True)
+    labels = torch.randint(0, c, (n,)).cuda()
+    mask = (torch.rand(n) < 0.6).cuda()
+    idx = torch.nonzero(mask).squeeze(1)
+    loss = nll_log_softmax(out, labels, mask)
+    ref = torch.nn.functional.nll_loss(torch.log_softmax(out2, 1)[idx], labels[idx])
+    (2.5 * loss).backward()
+    (2.5 * ref).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-5 * abs(float(ref))
+    np.testing.assert_allclose(out.grad.cpu().numpy(), out2.grad.cpu().numpy(), rtol=2e-4, atol=1e-8)
+    # no mask = every row
+    l2 = nll_log_softmax(out.detach(), labels)
+    r2 = torch.nn.functional.nll_loss(torch.log_softmax(out2.detach(), 1), labels)
+    assert abs(float(l2) - float(r2)) <= 2e-5 * abs(float(r2))
