@@ -35,6 +35,13 @@ class GCN(nn.Module):
         self.xX_param = Parameter(torch.zeros(1, 1, device=L.device))
         if model_type == "acmgcnpp":
             self.mlpX.reset_parameters()
+        # Inter-layer fusion.  With variant=False every channel output is a
+        # relu (O_k >= 0) and the attention weights are positive, so Y = c * sum_k att_k O_k >= 0
+        # element-wise: the reference's F.relu(fea1) (models.py:160) is the identity, and its
+        # backward mask (fea1 > 0) only zeroes gradient entries that cannot influence anything
+        # (Y_f == 0 implies O_k,f == 0 for all k, whose relu masks already block that path).
+        # Skipping it saves two [N, hidden] fp32 passes per step; results are bit-identical.
+        self.skip_identity_relu = True
 
     def forward(self, x, adj_low, adj_high, adj_low_unnormalized):
         x = F.dropout(x, self.dropout, training=self.training)
@@ -42,7 +49,9 @@ class GCN(nn.Module):
         if self.model_type == "acmgcnpp":
             xX = F.dropout(F.relu(self.mlpX(x, input_tensor=True)), self.dropout, training=self.training)
         fea1 = self.gcns[0](x, adj_low, adj_high, adj_low_unnormalized)
-        fea1 = F.dropout(F.relu(fea1), self.dropout, training=self.training)
+        if not (self.skip_identity_relu and not self.gcns[0].variant):
+            fea1 = F.relu(fea1)
+        fea1 = F.dropout(fea1, self.dropout, training=self.training)
         if xX is not None:
             fea1 = fea1 + xX
         return self.gcns[1](fea1, adj_low, adj_high, adj_low_unnormalized)

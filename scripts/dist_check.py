@@ -1,0 +1,77 @@
+"""Multi-GPU parity check (run under torchrun, one rank per GPU): the row-partitioned model
+(NCCL all-gather of the operand tables, all-reduce of parameter gradients) must reproduce the
+single-GPU model on the same graph, inputs and parameters.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 scripts/dist_check.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    dist.init_process_group("nccl", device_id=dev)
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import layers as L
+    from acm_gnn_b200.dist import RowPartition, attach
+    from acm_gnn_b200.functional import nll_log_softmax
+    L.device = dev
+    ok_all = True
+    for mode, variant, n in (("fp32", False, 5003), ("bf16", False, 5003), ("fp32", True, 4096)):
+        os.environ["ACMB200_DTYPE"] = mode
+        fin, hid, ncls = 48, 64, 7
+        g = torch.Generator(device=dev); g.manual_seed(5)
+        src = torch.randint(0, n, (40000,), generator=g, device=dev)
+        dst = torch.randint(0, n, (40000,), generator=g, device=dev)
+        keep = src != dst
+        row, col = torch.cat([src[keep], dst[keep]]), torch.cat([dst[keep], src[keep]])
+        key = torch.unique(row * n + col)
+        row, col = key // n, key % n
+        x = torch.rand(n, fin, generator=g, device=dev)
+        labels = torch.randint(0, ncls, (n,), generator=g, device=dev)
+        mask = (torch.rand(n, generator=g, device=dev) < 0.6).to(torch.uint8)
+        ntr = int(mask.sum().item())
+        op = A.AcmOperator.from_edges(row, col, n)
+
+        def build():
+            torch.manual_seed(42)
+            return A.GCN(fin, hid, ncls, 2, n, 0.0, "acmgcn", 0, variant=variant).to(dev)
+
+        # single-GPU reference (every rank computes it redundantly)
+        m1 = build()
+        out1 = m1(x, op, None, None)
+        nll_log_softmax(out1, labels, mask, n_train=ntr).backward()
+        # row-partitioned
+        part = RowPartition(n)
+        m2 = attach(build(), part)
+        opl = op.partition(part.r0, part.r1)
+        out2 = m2(x[part.r0:part.r1].contiguous(), opl, None, None)
+        nll_log_softmax(out2, labels[part.r0:part.r1].contiguous(), mask[part.r0:part.r1].contiguous(), n_train=ntr).backward()
+        torch.cuda.synchronize()
+        tol = 2e-5 if mode == "fp32" else 3e-2
+        e_out = float((out2 - out1[part.r0:part.r1]).abs().max() / out1.abs().max())
+        worst = 0.0
+        for (k, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+            if p1.grad is None or k in ("fea_param", "xX_param"):
+                continue
+            worst = max(worst, float((p1.grad - p2.grad).norm() / p1.grad.norm().clamp_min(1e-20)))
+        ok = e_out <= tol and worst <= (2e-4 if mode == "fp32" else 0.1)
+        t = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok_all = ok_all and bool(t.item())
+        if rank == 0:
+            print(f"dist_check world={world} mode={mode} variant={variant} n={n}: out rel.err {e_out:.2e}, worst grad rel.fro {worst:.2e} -> {'OK' if t.item() else 'FAIL'}", flush=True)
+    if rank == 0:
+        print("DIST_CHECK", "PASS" if ok_all else "FAIL", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if ok_all else 1)
+
+
+if __name__ == "__main__":
+    main()
