@@ -89,7 +89,8 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int m, int n, int a_mn_m
 struct TnParams {
   int64_t m, n, k;       // problem
   int bn;                // UMMA_N / B box rows (multiple of 16, <= 256)
-  int n_tiles, stages, tmem_cols;
+  int n_tiles, stages, tmem_cols, acc_cols;
+  int64_t total_tiles;
   // MODE 0 (forward): bf16 outputs split at ncols0
   __nv_bfloat16* c0; int64_t ldc0; int ncols0;
   __nv_bfloat16* c1; int64_t ldc1;
@@ -98,22 +99,29 @@ struct TnParams {
   float* cf; int64_t ldcf; int vec_ok;
 };
 
+constexpr int kTnEpiWarps = 8;                       // two warps per 32-lane TMEM quadrant
+constexpr int kTnThreads = 64 + 32 * kTnEpiWarps;    // + producer warp + MMA warp
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent kernel: one CTA per SM walks tiles (n fastest, so neighbouring CTAs share the A
+// tile in L2); the TMA/MMA ring runs continuously across tiles and the accumulator is double
+// buffered in TMEM, so the epilogue of tile t overlaps the main loop of tile t+1.
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kTnThreads, 1)
 tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = BM * BK * 2;
   const uint32_t b_bytes = (uint32_t)p.bn * BK * 2;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
-  const uint32_t bar_base = base + p.stages * stage_bytes;  // full[s], empty[s], tmem_full, tmem_ptr
-  const uint32_t tmem_full = bar_base + 16 * p.stages;
-  const uint32_t tmem_slot = tmem_full + 8;
+  const uint32_t bar_base = base + p.stages * stage_bytes;        // full[s] | empty[s]
+  const uint32_t tfull = bar_base + 16 * p.stages;                // tmem_full[2]
+  const uint32_t tempty = tfull + 16;                             // tmem_empty[2]
+  const uint32_t tmem_slot = tempty + 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_n = blockIdx.x % p.n_tiles;
-  const int64_t tile_m = blockIdx.x / p.n_tiles;
-  const int64_t m0 = tile_m * BM;
-  const int n0 = tile_n * p.bn;
   const int kb_total = (int)((p.k + BK - 1) / BK);
 
   if (threadIdx.x == 0) {
@@ -121,7 +129,10 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_init(bar_base + 8 * s, 1);
       mbar_init(bar_base + 8 * (p.stages + s), 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull + 8 * a, 1);
+      mbar_init(tempty + 8 * a, kTnEpiWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -141,13 +152,17 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < kb_total; ++kb) {
-        mbar_wait(bar_base + 8 * (p.stages + s), ph ^ 1);
-        const uint32_t full = bar_base + 8 * s;
-        mbar_expect_tx(full, a_bytes + b_bytes);
-        tma_load_2d(base + s * stage_bytes, &tmA, kb * BK, (int)m0, full);
-        tma_load_2d(base + s * stage_bytes + a_bytes, &tmB, kb * BK, n0, full);
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile % p.n_tiles) * p.bn;
+        const int m0 = (int)((tile / p.n_tiles) * BM);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(bar_base + 8 * (p.stages + s), ph ^ 1);
+          const uint32_t full = bar_base + 8 * s;
+          mbar_expect_tx(full, a_bytes + b_bytes);
+          tma_load_2d(base + s * stage_bytes, &tmA, kb * BK, m0, full);
+          tma_load_2d(base + s * stage_bytes + a_bytes, &tmB, kb * BK, n0, full);
+          if (++s == p.stages) { s = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -155,65 +170,84 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const uint32_t idesc = make_idesc(BM, p.bn, 0, 0);
       int s = 0;
       uint32_t ph = 0;
-      for (int kb = 0; kb < kb_total; ++kb) {
-        mbar_wait(bar_base + 8 * s, ph);
+      int t = 0;
+      for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+        const int a = t & 1;
+        mbar_wait(tempty + 8 * a, ((t >> 1) & 1) ^ 1);   // epilogue drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + s * stage_bytes, sb = sa + a_bytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.acc_cols);
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(bar_base + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * stage_bytes, sb = sa + a_bytes;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major, 128B swizzle: rows are 128 B apart, 8-row groups 1024 B apart (SBO);
-          // stepping K by 16 bf16 = +32 B inside the swizzle row
-          const uint64_t ad = make_desc(sa + k * UMMA_K * 2, 16, 1024);
-          const uint64_t bd = make_desc(sb + k * UMMA_K * 2, 16, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major, 128B swizzle: rows are 128 B apart, 8-row groups 1024 B apart (SBO);
+            // stepping K by 16 bf16 = +32 B inside the swizzle row
+            const uint64_t ad = make_desc(sa + k * UMMA_K * 2, 16, 1024);
+            const uint64_t bd = make_desc(sb + k * UMMA_K * 2, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(bar_base + 8 * (p.stages + s));  // frees the smem stage when the MMAs retire
+          if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-        umma_commit(bar_base + 8 * (p.stages + s));  // frees the smem stage when the MMAs retire
-        if (++s == p.stages) { s = 0; ph ^= 1; }
+        umma_commit(tfull + 8 * a);  // accumulator complete
       }
-      umma_commit(tmem_full);  // accumulator complete
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps of a
+    // quadrant take alternating 32-column chunks
     const int q = warp & 3;
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.m;
-    for (int c = 0; c < p.bn; c += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      if (!row_ok) continue;
-      if (MODE == 0) {
+    const int half = (warp - 2) >> 2;
+    int t = 0;
+    for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+      const int a = t & 1;
+      const int n0 = (int)(tile % p.n_tiles) * p.bn;
+      const int64_t m0 = (tile / p.n_tiles) * BM;
+      mbar_wait(tfull + 8 * a, (t >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.m;
+      for (int c = half * 32; c < p.bn; c += 64) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.acc_cols + c), r);
+        if (!row_ok) continue;
+        if (MODE == 0) {
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int j = n0 + c + g8 * 8;
-          if (c + g8 * 8 >= p.bn || j >= p.n) continue;
-          float v[8];
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int j = n0 + c + g8 * 8;
+            if (c + g8 * 8 >= p.bn || j >= p.n) continue;
+            float v[8];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            v[t] = __uint_as_float(r[g8 * 8 + t]);
-            if (j < p.relu_cols) v[t] = fmaxf(v[t], 0.f);
+            for (int u = 0; u < 8; ++u) {
+              v[u] = __uint_as_float(r[g8 * 8 + u]);
+              if (j < p.relu_cols) v[u] = fmaxf(v[u], 0.f);
+            }
+            __nv_bfloat16* dst = (j < p.ncols0) ? p.c0 + row * p.ldc0 + j : p.c1 + row * p.ldc1 + (j - p.ncols0);
+            *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
           }
-          __nv_bfloat16* dst = (j < p.ncols0) ? p.c0 + row * p.ldc0 + j : p.c1 + row * p.ldc1 + (j - p.ncols0);
-          *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
-        }
-      } else {
-        float* dst = p.cf + row * p.ldcf + n0 + c;
+        } else {
+          float* dst = p.cf + row * p.ldcf + n0 + c;
 #pragma unroll
-        for (int g4 = 0; g4 < 8; ++g4) {
-          const int cc = c + g4 * 4;
-          const int j = n0 + cc;
-          if (cc >= p.bn || j >= p.n) continue;
-          if (p.vec_ok && j + 4 <= p.n) {
-            *reinterpret_cast<float4*>(dst + g4 * 4) = make_float4(__uint_as_float(r[g4 * 4]), __uint_as_float(r[g4 * 4 + 1]),
-                                                                  __uint_as_float(r[g4 * 4 + 2]), __uint_as_float(r[g4 * 4 + 3]));
-          } else {
+          for (int g4 = 0; g4 < 8; ++g4) {
+            const int cc = c + g4 * 4;
+            const int j = n0 + cc;
+            if (cc >= p.bn || j >= p.n) continue;
+            if (p.vec_ok && j + 4 <= p.n) {
+              *reinterpret_cast<float4*>(dst + g4 * 4) = make_float4(__uint_as_float(r[g4 * 4]), __uint_as_float(r[g4 * 4 + 1]),
+                                                                    __uint_as_float(r[g4 * 4 + 2]), __uint_as_float(r[g4 * 4 + 3]));
+            } else {
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              if (j + t < p.n) dst[g4 * 4 + t] = __uint_as_float(r[g4 * 4 + t]);
+              for (int u = 0; u < 4; ++u)
+                if (j + u < p.n) dst[g4 * 4 + u] = __uint_as_float(r[g4 * 4 + u]);
+            }
           }
         }
       }
+      // all of this warp's TMEM reads have completed (tcgen05.wait::ld in tmem_ld32)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + 8 * a);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -378,6 +412,12 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
 
 static int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
 
+static int sm_count() {
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
 template <int MODE>
 static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, TnParams p, cudaStream_t st) {
   if (p.m == 0) return 0;
@@ -385,24 +425,26 @@ static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, TnP
   bn = (bn + 15) / 16 * 16;
   p.bn = bn;
   p.n_tiles = (int)((p.n + bn - 1) / bn);
-  p.tmem_cols = pow2_cols(bn);
+  p.acc_cols = pow2_cols(bn);
+  p.tmem_cols = 2 * p.acc_cols;
   const uint32_t stage_bytes = BM * BK * 2 + (((uint32_t)bn * BK * 2 + 1023u) & ~1023u);
-  int stages = (int)(100 * 1024 / stage_bytes);
-  if (stages > 6) stages = 6;
+  int stages = (int)(200 * 1024 / stage_bytes);
+  if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 64 + 1024;
   CUtensorMap ma, mb;
   int rc = make_map(&ma, a, (uint64_t)p.k, (uint64_t)p.m, (uint64_t)lda, BK, BM, "A operand");
   if (rc) return rc;
   rc = make_map(&mb, b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)ldb, BK, (uint32_t)bn, "B operand");
   if (rc) return rc;
   const int64_t m_tiles = (p.m + BM - 1) / BM;
-  const int64_t grid = m_tiles * p.n_tiles;
-  ACM_CHECK_ARG(grid < (1ll << 31), "tcgen05 GEMM: grid too large");
+  ACM_CHECK_ARG(m_tiles * BM < (1ll << 31), "tcgen05 GEMM: more than 2^31 rows");
+  p.total_tiles = m_tiles * p.n_tiles;
+  const int64_t grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
   cudaError_t e = cudaFuncSetAttribute(tn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tcgen05 GEMM: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-  tn_kernel<MODE><<<(unsigned)grid, kThreads, smem, st>>>(ma, mb, p);
+  tn_kernel<MODE><<<(unsigned)grid, kTnThreads, smem, st>>>(ma, mb, p);
   ACM_LAUNCH_CHECK("tcgen05 gemm_tn");
   return 0;
 }
@@ -450,12 +492,7 @@ int tc_gemm_dw(const void* x, int64_t ldx, const void* dh, float* dwcat, int64_t
   const int kb_all = (int)((n + BK - 1) / BK);
   // one CTA per SM (190 KB of smem each): never more CTAs than SMs, or the doubly loaded SMs
   // set the critical path (measured: 150 CTAs on 148 SMs ran at half speed)
-  int sms = 148;
-  {
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  int splits = sms / tiles;
+  int splits = sm_count() / tiles;
   if (splits > kb_all) splits = kb_all;
   if (splits < 1) splits = 1;
   p.kb_per_split = (kb_all + splits - 1) / splits;

@@ -323,7 +323,10 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = nnz_global / (ms_per_step * 1e-3)
     peak_mem = torch.cuda.max_memory_allocated() / 1e9
-    final_loss = float(loss.item())
+    lt = loss.detach().clone().to(torch.float64)
+    if world > 1:
+        dist.all_reduce(lt)  # per-rank partial sums of the (globally normalised) loss
+    final_loss = float(lt.item())
 
     # ---- roofline of the dominant kernel: fused SpMM + attention + mix, layer 0 ---------------
     summ = timer.summary()
