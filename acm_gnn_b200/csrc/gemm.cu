@@ -14,7 +14,58 @@ int tc_gemm_dw(const void* x, int64_t ldx, const void* dh, float* dwcat, int64_t
                cudaStream_t st);
 int tc_gemm_dx(const void* dh, const void* wcat, float* dx, int64_t lddx, int64_t n, int64_t fin, int64_t fp,
                cudaStream_t st);
+int tc_gemm_atb(const void* a, int64_t lda, const void* b, int64_t ldb, float* c, int64_t ldc,
+                int64_t k_rows, int64_t m, int64_t ncols, cudaStream_t st);
+int tc_gemm_ab(const void* a, int64_t lda, const void* b_nk, int64_t ldb, void* c, int64_t ldc,
+               int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st);
 }  // namespace acm
+
+extern "C" int acm_gemm_ab(int impl, int dtype, const void* a, int64_t lda, const void* b_kn, int64_t ldb_kn,
+                           const void* b_nk, int64_t ldb_nk, void* c, int64_t ldc,
+                           int64_t m, int64_t n, int64_t k, int relu, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "gemm_ab: bad dtype %d", dtype);
+  ACM_CHECK_ARG(a && c, "gemm_ab: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == ACM_GEMM_TCGEN05) {
+    ACM_CHECK_ARG(dtype == ACM_BF16 && b_nk, "gemm_ab: the tcgen05 path needs bf16 storage and the K-major B operand");
+    ACM_CHECK_ARG(n % 8 == 0, "gemm_ab: tcgen05 path needs n %% 8 == 0");
+    return tc_gemm_ab(a, lda, b_nk, ldb_nk, c, ldc, m, n, k, relu, st);
+  }
+  ACM_CHECK_ARG(impl == ACM_GEMM_SIMT && b_kn, "gemm_ab: SIMT path needs the [k,n] B operand");
+  GemmParams p{};
+  p.a = a; p.a_rs = lda; p.a_cs = 1;
+  p.b = b_kn; p.b_rs = ldb_kn; p.b_cs = 1;
+  p.c0 = c; p.ldc0 = ldc; p.ncols0 = n; p.c1 = nullptr; p.ldc1 = 0;
+  p.m = m; p.n = n; p.k = k;
+  p.c_bf16 = (dtype == ACM_BF16); p.relu_cols = relu ? (int)n : 0; p.atomic = 0;
+  return gemm_simt(dtype, p, 1, st);
+}
+
+extern "C" int acm_gemm_atb(int impl, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
+                            float* c, int64_t ldc, int64_t k_rows, int64_t m, int64_t n, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "gemm_atb: bad dtype %d", dtype);
+  ACM_CHECK_ARG(a && b && c, "gemm_atb: null pointer");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (impl == ACM_GEMM_TCGEN05) {
+    ACM_CHECK_ARG(dtype == ACM_BF16, "gemm_atb: the tcgen05 path needs bf16 storage");
+    return tc_gemm_atb(a, lda, b, ldb, c, ldc, k_rows, m, n, st);
+  }
+  ACM_CHECK_ARG(impl == ACM_GEMM_SIMT, "gemm_atb: unknown impl %d", impl);
+  GemmParams p{};
+  p.a = a; p.a_rs = 1; p.a_cs = lda;
+  p.b = b; p.b_rs = ldb; p.b_cs = 1;
+  p.c0 = c; p.ldc0 = ldc; p.ncols0 = n; p.c1 = nullptr; p.ldc1 = 0;
+  p.m = m; p.n = n; p.k = k_rows;
+  p.c_bf16 = 0; p.relu_cols = 0; p.atomic = 1;
+  const int64_t tiles = ((m + 63) / 64) * ((n + 63) / 64);
+  int64_t splits = (148 * 8 + tiles - 1) / tiles;
+  const int64_t max_splits = (k_rows + 255) / 256;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  return gemm_simt(dtype, p, (int)splits, st);
+}
 
 extern "C" int acm_gemm_xw_fwd(int impl, int dtype, const void* x, int64_t ldx, const void* wcat, const void* wcat_t,
                                void* h_lh, void* h_i, int64_t n, int64_t fin, int64_t fp, int relu_lh, void* stream) {

@@ -470,12 +470,13 @@ int tc_gemm_dx(const void* dh, const void* wcat, float* dx, int64_t lddx, int64_
   return tc::launch_tn<1>(dh, 3 * fp, wcat, 3 * fp, p, st);
 }
 
-int tc_gemm_dw(const void* x, int64_t ldx, const void* dh, float* dwcat, int64_t n, int64_t fin, int64_t fp,
-               cudaStream_t st) {
+// C[m, ncols] (fp32, row stride ldc, atomically accumulated) += A[k_rows, m]^T . B[k_rows, ncols]
+int tc_gemm_atb(const void* a, int64_t lda, const void* b, int64_t ldb, float* c, int64_t ldc,
+                int64_t k_rows, int64_t m, int64_t ncols, cudaStream_t st) {
   using namespace tc;
-  if (n == 0) return 0;
+  if (k_rows == 0 || m == 0 || ncols == 0) return 0;
   NtParams p{};
-  p.m = fin; p.n = 3 * fp; p.k = n;
+  p.m = m; p.n = ncols; p.k = k_rows;
   int bn = (int)(p.n < 256 ? p.n : 256);
   bn = (bn + 15) / 16 * 16;
   p.bn = bn;
@@ -483,13 +484,13 @@ int tc_gemm_dw(const void* x, int64_t ldx, const void* dh, float* dwcat, int64_t
   p.m_tiles = (int)((p.m + BM - 1) / BM);
   p.n_tiles = (int)((p.n + bn - 1) / bn);
   p.tmem_cols = pow2_cols(bn);
-  p.c = dwcat; p.ldc = 3 * fp;
+  p.c = c; p.ldc = ldc;
   const uint32_t stage_bytes = (2 + p.n_chunks) * BK * 128;
   int stages = (int)(190 * 1024 / stage_bytes);
   if (stages > 8) stages = 8;
   p.stages = stages;
   const int tiles = p.m_tiles * p.n_tiles;
-  const int kb_all = (int)((n + BK - 1) / BK);
+  const int kb_all = (int)((k_rows + BK - 1) / BK);
   // one CTA per SM (190 KB of smem each): never more CTAs than SMs, or the doubly loaded SMs
   // set the critical path (measured: 150 CTAs on 148 SMs ran at half speed)
   int splits = sm_count() / tiles;
@@ -500,15 +501,31 @@ int tc_gemm_dw(const void* x, int64_t ldx, const void* dh, float* dwcat, int64_t
   const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + 1024;
   CUtensorMap ma, mb;
   // MN-major operands: inner dimension = feature columns, outer = node rows (K)
-  int rc = make_map(&ma, x, (uint64_t)fin, (uint64_t)n, (uint64_t)ldx, 64, BK, "X (dW A operand)");
+  int rc = make_map(&ma, a, (uint64_t)m, (uint64_t)k_rows, (uint64_t)lda, 64, BK, "A^T operand");
   if (rc) return rc;
-  rc = make_map(&mb, dh, (uint64_t)(3 * fp), (uint64_t)n, (uint64_t)(3 * fp), 64, BK, "dH (dW B operand)");
+  rc = make_map(&mb, b, (uint64_t)ncols, (uint64_t)k_rows, (uint64_t)ldb, 64, BK, "B operand (MN-major)");
   if (rc) return rc;
   cudaError_t e = cudaFuncSetAttribute(nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tcgen05 GEMM: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
   nt_kernel<<<(unsigned)(tiles * splits), kThreads, smem, st>>>(ma, mb, p);
   ACM_LAUNCH_CHECK("tcgen05 gemm_nt");
   return 0;
+}
+
+int tc_gemm_dw(const void* x, int64_t ldx, const void* dh, float* dwcat, int64_t n, int64_t fin, int64_t fp,
+               cudaStream_t st) {
+  return tc_gemm_atb(x, ldx, dh, 3 * fp, dwcat, 3 * fp, n, fin, 3 * fp, st);
+}
+
+// C[m, n] (bf16, row stride ldc) = A[m,k] . B^T with B given K-major as b_nk [n, k]
+int tc_gemm_ab(const void* a, int64_t lda, const void* b_nk, int64_t ldb, void* c, int64_t ldc,
+               int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st) {
+  tc::TnParams p{};
+  p.m = m; p.n = n; p.k = k;
+  p.c0 = (__nv_bfloat16*)c; p.ldc0 = ldc; p.ncols0 = (int)n;
+  p.c1 = nullptr; p.ldc1 = 0;
+  p.relu_cols = relu ? (int)n : 0;
+  return tc::launch_tn<0>(a, lda, b_nk, ldb, p, st);
 }
 
 }  // namespace acm

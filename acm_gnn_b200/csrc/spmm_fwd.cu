@@ -24,7 +24,7 @@ struct FwdParams {
   const void* h_i;
   const void* o_s;
   const float* pack;
-  int k, ln, variant, f, vec_y;
+  int k, ln, variant, f, vec_y, pre_agg;
   float out_scale;
   float* y;
   int64_t ldy;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
   const bool valid = row < p.n_rows;
 
   int64_t e = 0, e1 = 0;
-  if (valid) {
+  if (valid && !p.pre_agg) {
     e = __ldg(p.rowptr + row);
     e1 = __ldg(p.rowptr + row + 1);
   }
@@ -143,6 +143,12 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
       b.load(reinterpret_cast<const T*>(p.h_i) + row * FP + gl * 8);
       a.to_float(hs);
       b.to_float(hi);
+      if (p.pre_agg) {
+        // aggregate-first order: the table row already holds [S_L | S_H] = [(AX)W_L | (X-AX)W_H]
+        Slice8<T> c;
+        c.load(tab + (p.row0 + row) * TW);
+        c.to_float(accL);
+      }
     } else {
 #pragma unroll
       for (int t = 0; t < 8; ++t) hs[t] = hi[t] = 0.f;
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       float sl = rs * accL[t];
-      float sh = hs[t] - rs * accH[t];
+      float sh = hs[t] - rs * accH[t];  // pre_agg: accH == 0, so S_H = table value
       if (!p.variant) {
         sl = fmaxf(sl, 0.f);
         sh = fmaxf(sh, 0.f);
@@ -281,12 +287,14 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
   ACM_CHECK_ARG(k_channels == 3 || k_channels == 4, "spmm_mix_fwd: k_channels must be 3 or 4");
   ACM_CHECK_ARG(f >= 1 && f <= fp, "spmm_mix_fwd: need 1 <= f <= fp");
   ACM_CHECK_ARG(k_channels == 3 || o_s != nullptr, "spmm_mix_fwd: 4 channels need o_s");
-  ACM_CHECK_ARG(rowptr && col && table && h_i && pack && y && att, "spmm_mix_fwd: null pointer");
+  ACM_CHECK_ARG(table && h_i && pack && y && att, "spmm_mix_fwd: null pointer");
+  ACM_CHECK_ARG((rowptr && col) || (!rowptr && !col), "spmm_mix_fwd: rowptr and col must both be given or both be NULL");
   FwdParams p;
   p.n_rows = n_rows; p.row0 = row0; p.rowptr = rowptr; p.col = col; p.val = val; p.rowscale = rowscale;
   p.table = table; p.h_i = h_i; p.o_s = o_s; p.pack = pack; p.k = k_channels; p.ln = ln_live;
   p.variant = variant; p.f = f; p.out_scale = out_scale; p.y = y; p.ldy = ldy; p.o_save = o_save;
   p.att = att; p.sig = sig;
+  p.pre_agg = (rowptr == nullptr);
   p.vec_y = (f % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int mode = (k_channels == 4 || ln_live) ? 1 : 0;

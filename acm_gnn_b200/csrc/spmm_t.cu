@@ -158,7 +158,90 @@ spmm_plain_kernel(int64_t n_rows, const int64_t* __restrict__ rowptr, const int3
   }
 }
 
+// Aggregate-first order (A(XW) = (AX)W): Z = A.X and D = X - Z for the
+// own rows, one gather of the (narrower) INPUT row per stored edge.
+template <typename T, int FP>
+__global__ void __launch_bounds__(kTWarps * 32)
+spmm_agg_first_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                      const float* __restrict__ val, const T* __restrict__ table, T* __restrict__ z_out,
+                      T* __restrict__ d_out) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPW = 32 / LANES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LANES, gl = lane % LANES;
+  const int64_t row = ((int64_t)blockIdx.x * kTWarps + warp) * RPW + sub;
+  if (row >= n_rows) return;
+  int64_t e = __ldg(rowptr + row);
+  const int64_t e1 = __ldg(rowptr + row + 1);
+  const T* tab = table + gl * 8;
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  constexpr int U = 8;  // narrower rows than the [HL|HH] table: keep the same bytes in flight
+  for (; e + U <= e1; e += U) {
+    int32_t c[U];
+    float w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      c[u] = __ldg(col + e + u);
+      w[u] = val ? __ldg(val + e + u) : 1.f;
+    }
+    Slice8<T> v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u].load(tab + (int64_t)c[u] * FP);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float f[8];
+      v[u].to_float(f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[t] = fmaf(w[u], f[t], acc[t]);
+    }
+  }
+  for (; e < e1; ++e) {
+    const int32_t c = __ldg(col + e);
+    const float w = val ? __ldg(val + e) : 1.f;
+    Slice8<T> v;
+    v.load(tab + (int64_t)c * FP);
+    float f[8];
+    v.to_float(f);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = fmaf(w, f[t], acc[t]);
+  }
+  float self[8], d[8];
+  {
+    Slice8<T> s;
+    s.load(tab + (row0 + row) * FP);
+    s.to_float(self);
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) d[t] = self[t] - acc[t];
+  Slice8<T>::store(z_out + row * FP + gl * 8, acc);
+  Slice8<T>::store(d_out + row * FP + gl * 8, d);
+}
+
 }  // namespace acm
+
+extern "C" int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row0,
+                                  const int64_t* rowptr, const int32_t* col, const float* val,
+                                  const void* table, void* z_out, void* d_out, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_agg_first: bad dtype %d", dtype);
+  ACM_CHECK_ARG(rowptr && col && table && z_out && d_out, "spmm_agg_first: null pointer");
+  if (n_rows == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define ACM_A_LAUNCH(TT)                                                                          \
+  ACM_DISPATCH_FP(fp, {                                                                           \
+    constexpr int RPB = (32 / (FP / 8)) * kTWarps;                                                \
+    const int64_t blocks = (n_rows + RPB - 1) / RPB;                                              \
+    ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_agg_first: too many rows");                         \
+    spmm_agg_first_kernel<TT, FP><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                     \
+        n_rows, row0, rowptr, col, val, (const TT*)table, (TT*)z_out, (TT*)d_out);                \
+  })
+  if (dtype == ACM_BF16) { ACM_A_LAUNCH(__nv_bfloat16); } else { ACM_A_LAUNCH(float); }
+#undef ACM_A_LAUNCH
+  ACM_LAUNCH_CHECK("spmm_agg_first");
+  return 0;
+}
 
 extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
                               const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,

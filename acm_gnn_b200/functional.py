@@ -42,6 +42,7 @@ class LayerConfig:
     out_scale: float = 3.0
     dtype: str = "bf16"        # storage of feature tables: "bf16" | "fp32" (accumulation is fp32)
     gemm: str = "auto"         # "simt" | "tcgen05" | "auto"
+    reorder: str = "env"       # aggregate-first order A(XW) = (AX)W: "auto" | "off" | "env" (ACMB200_REORDER)
     dist: Optional[object] = None   # acm_gnn_b200.dist.RowPartition or None
 
     def storage(self):
@@ -62,6 +63,28 @@ def tc_available() -> bool:
     """The tcgen05 GEMM kernels (gemm_tc.cu) are the default for bf16 storage; set
     ACMB200_GEMM=simt to force the CUDA-core path."""
     return True
+
+
+def reorder_enabled(cfg: LayerConfig) -> bool:
+    r = cfg.reorder
+    if r == "env":
+        r = os.environ.get("ACMB200_REORDER", "off").lower()
+    if r in ("auto", "1", "on"):
+        return True
+    if r in ("off", "0"):
+        return False
+    raise ValueError(f"ACMB200_REORDER={r!r}: expected auto or off")
+
+
+def use_aggregate_first(cfg: LayerConfig, fin: int, fp: int, x_needs_grad: bool) -> bool:
+    """SURVEY 8(f) rank 4.  A(XW_L) = (AX)W_L and HH - A(XW_H) = (X - AX)W_H: aggregate the
+    layer INPUT once (Fin wide) instead of the [HL|HH] table (2*out_features wide).  Valid when
+    the relu sits after the aggregation (variant 0); chosen when the input row is not wider
+    than the table row and the input needs no gradient (first layer) -- then the backward
+    needs no transposed aggregation at all: dW_L = (AX)^T dS_L, dW_H = (X-AX)^T dS_H."""
+    if not reorder_enabled(cfg) or cfg.variant or x_needs_grad or fin > 256:
+        return False
+    return padded_width(fin) <= 2 * fp
 
 
 def default_dtype() -> str:
@@ -124,26 +147,54 @@ class AcmLayerFunction(torch.autograd.Function):
         wcat = build_wcat(fp, f, (w_low, w_high, w_mlp), tdt)
 
         impl = cfg.gemm_impl(fin)
-        # staging copy of the layer input in the storage dtype (row stride padded to 8)
-        if cfg.dtype == "bf16":
-            ldx = (fin + 7) // 8 * 8
-            xs = torch.empty(n, ldx, dtype=tdt, device=dev)
-            xc = x.detach().contiguous()
-            _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, xs.data_ptr(), cdt, ldx, st)
-        else:
-            xs = x.detach().contiguous()
-            ldx = fin
-        wcat_t = None
-        if impl == _lib.GEMM_TCGEN05:
-            wcat_t = torch.zeros(3 * fp, ldx, dtype=tdt, device=dev)
-            wcat_t[:, :fin] = wcat.t()
-
+        agg_first = use_aggregate_first(cfg, fin, fp, bool(ctx.needs_input_grad[2]))
         h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
         h_i = torch.empty(n, fp, dtype=tdt, device=dev)
-        _lib.call("acm_gemm_xw_fwd", impl, cdt, xs.data_ptr(), ldx, wcat.data_ptr(), _lib.ptr(wcat_t),
-                  h_lh.data_ptr(), h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
-
-        table = h_lh if cfg.dist is None else cfg.dist.all_gather_rows(h_lh)
+        z = d = wcat_t = None
+        if agg_first:
+            # ---- aggregate-first: Z = A X, D = X - Z, then [S_L|S_H|HI] = [Z W_L | D W_H | X W_I] ----
+            ldx = padded_width(fin)
+            xc = x.detach().contiguous()
+            if cfg.dtype == "fp32" and ldx == fin:
+                xs = xc
+            else:
+                xs = torch.empty(n, ldx, dtype=tdt, device=dev)
+                _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, xs.data_ptr(), cdt, ldx, st)
+            x_all = xs if cfg.dist is None else cfg.dist.all_gather_rows(xs)
+            z = torch.empty(n, ldx, dtype=tdt, device=dev)
+            d = torch.empty(n, ldx, dtype=tdt, device=dev)
+            _lib.call("acm_spmm_agg_first", cdt, ldx, n, op.row0, op.low.rowptr.data_ptr(), op.low.col.data_ptr(),
+                      op.low.val.data_ptr(), x_all.data_ptr(), z.data_ptr(), d.data_ptr(), st, tag=ldx)
+            del x_all
+            wp = torch.zeros(ldx, 3 * fp, dtype=tdt, device=dev)   # rows fin..ldx are zero
+            wp[:fin] = wcat
+            wt = wp.t().contiguous() if impl == _lib.GEMM_TCGEN05 else None  # [3fp, ldx], K-major
+            for k, (a_op, c_ptr, ldc) in enumerate(((z, h_lh.data_ptr(), 2 * fp),
+                                                    (d, h_lh[:, fp:].data_ptr(), 2 * fp),
+                                                    (xs, h_i.data_ptr(), fp))):
+                _lib.call("acm_gemm_ab", impl, cdt, a_op.data_ptr(), ldx, wp[:, k * fp:].data_ptr(), 3 * fp,
+                          0 if wt is None else wt[k * fp:].data_ptr(), ldx, c_ptr, ldc, n, fp, ldx, 0, st, tag=fp)
+            del wp, wt
+            table, csr = h_lh, (0, 0, 0)      # pre-aggregated: only the epilogue of the fused kernel runs
+            row0 = 0
+        else:
+            # staging copy of the layer input in the storage dtype (row stride padded to 8)
+            if cfg.dtype == "bf16":
+                ldx = (fin + 7) // 8 * 8
+                xs = torch.empty(n, ldx, dtype=tdt, device=dev)
+                xc = x.detach().contiguous()
+                _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, xs.data_ptr(), cdt, ldx, st)
+            else:
+                xs = x.detach().contiguous()
+                ldx = fin
+            if impl == _lib.GEMM_TCGEN05:
+                wcat_t = torch.zeros(3 * fp, ldx, dtype=tdt, device=dev)
+                wcat_t[:, :fin] = wcat.t()
+            _lib.call("acm_gemm_xw_fwd", impl, cdt, xs.data_ptr(), ldx, wcat.data_ptr(), _lib.ptr(wcat_t),
+                      h_lh.data_ptr(), h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
+            table = h_lh if cfg.dist is None else cfg.dist.all_gather_rows(h_lh)
+            csr = (op.low.rowptr.data_ptr(), op.low.col.data_ptr(), op.low.val.data_ptr())
+            row0 = op.row0
 
         o_s = None
         if K == 4:
@@ -164,8 +215,7 @@ class AcmLayerFunction(torch.autograd.Function):
         att = torch.empty(n, K, dtype=torch.float32, device=dev)
         sig = torch.empty(n, K, dtype=torch.float32, device=dev) if need_grad else None
         o_save = torch.empty(n, 2 * fp, dtype=tdt, device=dev) if need_grad else None
-        _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, op.row0,
-                  op.low.rowptr.data_ptr(), op.low.col.data_ptr(), op.low.val.data_ptr(), 0,
+        _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, row0, csr[0], csr[1], csr[2], 0,
                   table.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s), pack.data_ptr(),
                   K, int(cfg.ln_live), int(cfg.variant), float(cfg.out_scale),
                   y.data_ptr(), f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig), st, tag=fp)
@@ -174,17 +224,18 @@ class AcmLayerFunction(torch.autograd.Function):
         if need_grad:
             ctx.op, ctx.cfg = op, cfg
             ctx.dims = (n, fin, f, fp, K, ldx, impl)
+            ctx.agg_first = agg_first
             ctx.x_needs_grad = bool(ctx.needs_input_grad[2])
             ctx.n_ln = len(ln_flat)
             ctx.struc_rows = 0 if struc_low is None else struc_low.shape[0]
             # variant 1 needs the relu'd forward table (its positivity is the relu mask)
             ctx.save_for_backward(xs, wcat, wcat_t, h_i, o_save, att, sig, pack, o_s,
-                                  h_lh if cfg.variant else None)
+                                  h_lh if cfg.variant else None, z, d)
         return y, att
 
     @staticmethod
     def backward(ctx, g, _g_att):
-        xs, wcat, wcat_t, h_i, o_save, att, sig, pack, o_s, p_tab = ctx.saved_tensors
+        xs, wcat, wcat_t, h_i, o_save, att, sig, pack, o_s, p_tab, z, d = ctx.saved_tensors
         op, cfg = ctx.op, ctx.cfg
         n, fin, f, fp, K, ldx, impl = ctx.dims
         tdt, cdt = cfg.storage()
@@ -200,18 +251,26 @@ class AcmLayerFunction(torch.autograd.Function):
                   att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
                   float(cfg.out_scale), t_lh.data_ptr(), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(), st, tag=fp)
 
-        t_table = t_lh if cfg.dist is None else cfg.dist.all_gather_rows(t_lh)
-        _lib.call("acm_spmm_t_bwd", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
-                  op.low.val_t.data_ptr(), t_table.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(), st, tag=fp)
-        del t_table, t_lh
-
         dwcat = torch.zeros(fin, 3 * fp, dtype=torch.float32, device=dev)
-        _lib.call("acm_gemm_bwd_dw", impl, cdt, xs.data_ptr(), ldx, dh_all.data_ptr(), dwcat.data_ptr(), n, fin, fp, st, tag=fp)
         dx = None
-        if ctx.x_needs_grad:
-            dx = torch.empty(n, fin, dtype=torch.float32, device=dev)
-            _lib.call("acm_gemm_bwd_dx", impl, cdt, dh_all.data_ptr(), wcat.data_ptr(), _lib.ptr(wcat_t), ldx,
-                      dx.data_ptr(), fin, n, fin, fp, st, tag=fp)
+        if ctx.agg_first:
+            # dW_L = (AX)^T dS_L ; dW_H = (X - AX)^T dS_H ; dW_I = X^T dHI -- no transposed aggregation
+            for k, (a_op, b_ptr, ldb) in enumerate(((z, t_lh.data_ptr(), 2 * fp),
+                                                    (d, t_lh[:, fp:].data_ptr(), 2 * fp),
+                                                    (xs, dh_all[:, 2 * fp:].data_ptr(), 3 * fp))):
+                _lib.call("acm_gemm_atb", impl, cdt, a_op.data_ptr(), ldx, b_ptr, ldb,
+                          dwcat[:, k * fp:].data_ptr(), 3 * fp, n, fin, fp, st, tag=fp)
+        else:
+            t_table = t_lh if cfg.dist is None else cfg.dist.all_gather_rows(t_lh)
+            _lib.call("acm_spmm_t_bwd", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
+                      op.low.val_t.data_ptr(), t_table.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(), st, tag=fp)
+            del t_table
+            _lib.call("acm_gemm_bwd_dw", impl, cdt, xs.data_ptr(), ldx, dh_all.data_ptr(), dwcat.data_ptr(), n, fin, fp, st, tag=fp)
+            if ctx.x_needs_grad:
+                dx = torch.empty(n, fin, dtype=torch.float32, device=dev)
+                _lib.call("acm_gemm_bwd_dx", impl, cdt, dh_all.data_ptr(), wcat.data_ptr(), _lib.ptr(wcat_t), ldx,
+                          dx.data_ptr(), fin, n, fin, fp, st, tag=fp)
+        del t_lh
 
         d_struc = d_a_struc = None
         if K == 4:

@@ -98,6 +98,21 @@ int acm_gemm_bwd_dw(int impl, int dtype, const void* x, int64_t ldx, const void*
 int acm_gemm_bwd_dx(int impl, int dtype, const void* dh, const void* wcat, const void* wcat_t, int64_t ldwt,
                     float* dx, int64_t lddx, int64_t n, int64_t fin, int64_t fp, void* stream);
 
+/* Generic building blocks of the aggregate-first order (A(XW) = (AX)W):
+ * C[m,n] (T, row stride ldc) = A[m,k] . B, B given as b_kn [k,n] (CUDA-core path) and/or K-major
+ * b_nk [n,k] (tcgen05 path); optional relu. */
+int acm_gemm_ab(int impl, int dtype, const void* a, int64_t lda, const void* b_kn, int64_t ldb_kn,
+                const void* b_nk, int64_t ldb_nk, void* c, int64_t ldc,
+                int64_t m, int64_t n, int64_t k, int relu, void* stream);
+/* C[m,n] (fp32, row stride ldc, zeroed by caller, atomically accumulated) += A[k_rows,m]^T . B[k_rows,n] */
+int acm_gemm_atb(int impl, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
+                 float* c, int64_t ldc, int64_t k_rows, int64_t m, int64_t n, void* stream);
+/* Z = A_low . X and D = X - Z for the own rows (table = X of all nodes, T [*, fp]); one gather
+ * of the INPUT row per stored edge instead of the 2*out_features wide [HL|HH] row. */
+int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row0,
+                       const int64_t* rowptr, const int32_t* col, const float* val,
+                       const void* table, void* z_out, void* d_out, void* stream);
+
 /* ---- fused aggregation + channel attention + mix (THE hot kernel) -------------------
  * layers.py:176-204 + attention3/attention4 (94-152) in one launch:
  *   acc  = sum_j val_ij * table[col_ij]            (one gather of the [HL|HH] row per edge)
@@ -108,7 +123,9 @@ int acm_gemm_bwd_dx(int impl, int dtype, const void* dh, const void* wcat, const
  *   Y   = out_scale * sum_k att_k O_k
  * Rows: this call computes rows [0,n_rows) whose global ids are row0+r; `table` is the
  * full (all-gathered) table indexed by global column ids.  val/rowscale may be NULL (=1).
- * o_save/sig may be NULL (inference). */
+ * o_save/sig may be NULL (inference).
+ * rowptr == col == NULL selects the pre-aggregated mode of the aggregate-first order: the
+ * own rows of `table` already hold [S_L | S_H] and only the epilogue runs. */
 int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
                      const int64_t* rowptr, const int32_t* col, const float* val, const float* rowscale,
                      const void* table, const void* h_i, const void* o_s,

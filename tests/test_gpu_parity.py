@@ -290,3 +290,72 @@ def test_fused_nll_log_softmax_matches_torch(c):
     l2 = nll_log_softmax(out.detach(), labels)
     r2 = torch.nn.functional.nll_loss(torch.log_softmax(out2.detach(), 1), labels)
     assert abs(float(l2) - float(r2)) <= 2e-5 * abs(float(r2))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("fin,f", [(7, 64), (64, 256), (256, 256), (100, 64), (16, 8), (128, 100)])
+def test_aggregate_first_order_matches_oracle(fin, f, mode, monkeypatch):
+    """A(XW) = (AX)W.  With ACMB200_REORDER=auto a variant-0 layer whose
+    input needs no gradient aggregates the INPUT (Fin wide) and runs no transposed
+    aggregation in backward; results must match the oracle like the default order does."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    monkeypatch.setenv("ACMB200_REORDER", "auto")
+    torch.manual_seed(fin * 1000 + f)
+    n = 411
+    row, col = O.synthetic_edges(n - 2, 3000, seed=fin + f, zipf=0.6)
+    row = np.concatenate([row, [3, 7]])
+    col = np.concatenate([col, [3, 7]])
+    op_ref = O.build_operator(row, col, n)
+    os.environ["ACMB200_DTYPE"] = mode
+    layer = A.GraphConvolution(fin, f, n, "acmgcn", variant=False).cuda()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    x = torch.randn(n, fin)
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    timer = _lib.KernelTimer()
+    _lib.set_timer(timer)
+    try:
+        y = layer(x.cuda(), op, None, None)          # input without grad -> aggregate-first
+        w = torch.randn(n, f)
+        (y * w.cuda()).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_timer(None)
+    names = set(k.split(":")[0] for k in timer.spans)
+    assert "acm_spmm_agg_first" in names and "acm_spmm_t_bwd" not in names, names
+    yo, atto = _oracle_layer(p, x.clone(), op_ref, False)
+    (yo * w).sum().backward()
+    _close(y, yo, mode, "y")
+    _close(torch.cat([layer.att_low, layer.att_high, layer.att_mlp], 1), atto, mode, "att")
+    for k in ("weight_low", "weight_high", "weight_mlp", "att_vec_low", "att_vec_high", "att_vec_mlp", "att_vec"):
+        _close_grad(getattr(layer, k).grad, p[k].grad, mode, "d" + k)
+    # an input that needs grad (or variant 1) keeps the transform-first order
+    timer2 = _lib.KernelTimer()
+    _lib.set_timer(timer2)
+    try:
+        layer(x.cuda().requires_grad_(True), op, None, None).sum().backward()
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_timer(None)
+    assert "acm_spmm_agg_first" not in set(k.split(":")[0] for k in timer2.spans)
+
+
+@pytest.mark.parametrize("name", ["gcn_pt_acmgcn_v0", "gcn_geo_acmgcnp_v0_s1", "gcn_pt_acmgcnpp_v0"])
+def test_gcn_golden_with_aggregate_first(name, monkeypatch):
+    """Reference golden run reproduced with the aggregate-first order in layer 0 (input
+    features carry no gradient, as in the reference drivers)."""
+    monkeypatch.setenv("ACMB200_REORDER", "auto")
+    g = Golden(name)
+    model = _cuda_model(g, "fp32")
+    low, high, un = g.adjacency()
+    x = g.x.clone().cuda()
+    model.train()
+    out = model(x, low.cuda(), high.cuda(), un.cuda() if un is not None else None)
+    loss = torch.nn.functional.nll_loss(torch.log_softmax(out, 1)[g.idx_train.cuda()], g.labels.cuda()[g.idx_train.cuda()])
+    loss.backward()
+    _close(out, g.z["out"], "fp32", "out")
+    ref_grads = g.grads()
+    for k, p_ in model.named_parameters():
+        if k in ("fea_param", "xX_param") or ".bns." in k or ref_grads[k].size == 0:
+            continue
+        _close_grad(p_.grad, ref_grads[k], "fp32", "grad " + k)
