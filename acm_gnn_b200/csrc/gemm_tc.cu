@@ -99,6 +99,7 @@ struct TnParams {
   float* cf; int64_t ldcf; int vec_ok;
 };
 
+constexpr int kStgLd = 36;                           // staging row stride in words (32 + 4 pad)
 constexpr int kTnEpiWarps = 8;                       // two warps per 32-lane TMEM quadrant
 constexpr int kTnThreads = 64 + 32 * kTnEpiWarps;    // + producer warp + MMA warp
 
@@ -199,6 +200,7 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // quadrant take alternating 32-column chunks
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    float* stg = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw))) + (warp - 2) * (32 * kStgLd);
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
       const int a = t & 1;
@@ -206,43 +208,56 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int64_t m0 = (tile / p.n_tiles) * BM;
       mbar_wait(tfull + 8 * a, (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.m;
       for (int c = half * 32; c < p.bn; c += 64) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.acc_cols + c), r);
-        if (!row_ok) continue;
+        // transpose through a per-warp staging tile (row stride 36 words: conflict-free v4
+        // stores) so that global stores are row-contiguous full 32-byte sectors
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4)
+          *reinterpret_cast<uint4*>(stg + lane * kStgLd + g4 * 4) = make_uint4(r[g4 * 4], r[g4 * 4 + 1], r[g4 * 4 + 2], r[g4 * 4 + 3]);
+        __syncwarp();
         if (MODE == 0) {
+          // 4 lanes x 16 B (8 bf16) per row, 8 rows per pass
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const int j = n0 + c + g8 * 8;
-            if (c + g8 * 8 >= p.bn || j >= p.n) continue;
-            float v[8];
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2);
+            const int cc = (lane & 3) * 8;
+            const int64_t row = m0 + q * 32 + rr;
+            const int j = n0 + c + cc;
+            if (row >= p.m || c + cc >= p.bn || j >= p.n) continue;
+            const float4 v0 = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cc);
+            const float4 v1 = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cc + 4);
+            float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            if (j < p.relu_cols) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              v[u] = __uint_as_float(r[g8 * 8 + u]);
-              if (j < p.relu_cols) v[u] = fmaxf(v[u], 0.f);
+              for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
             }
             __nv_bfloat16* dst = (j < p.ncols0) ? p.c0 + row * p.ldc0 + j : p.c1 + row * p.ldc1 + (j - p.ncols0);
             *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
           }
         } else {
-          float* dst = p.cf + row * p.ldcf + n0 + c;
+          // 8 lanes x 16 B (4 fp32) per row, 4 rows per pass
 #pragma unroll
-          for (int g4 = 0; g4 < 8; ++g4) {
-            const int cc = c + g4 * 4;
-            const int j = n0 + cc;
-            if (cc >= p.bn || j >= p.n) continue;
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3);
+            const int cc = (lane & 7) * 4;
+            const int64_t row = m0 + q * 32 + rr;
+            const int j = n0 + c + cc;
+            if (row >= p.m || c + cc >= p.bn || j >= p.n) continue;
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cc);
+            float* dst = p.cf + row * p.ldcf + j;
             if (p.vec_ok && j + 4 <= p.n) {
-              *reinterpret_cast<float4*>(dst + g4 * 4) = make_float4(__uint_as_float(r[g4 * 4]), __uint_as_float(r[g4 * 4 + 1]),
-                                                                    __uint_as_float(r[g4 * 4 + 2]), __uint_as_float(r[g4 * 4 + 3]));
+              *reinterpret_cast<float4*>(dst) = v;
             } else {
+              const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                if (j + u < p.n) dst[g4 * 4 + u] = __uint_as_float(r[g4 * 4 + u]);
+                if (j + u < p.n) dst[u] = vv[u];
             }
           }
         }
+        __syncwarp();
       }
       // all of this warp's TMEM reads have completed (tcgen05.wait::ld in tmem_ld32)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -428,11 +443,12 @@ static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, TnP
   p.acc_cols = pow2_cols(bn);
   p.tmem_cols = 2 * p.acc_cols;
   const uint32_t stage_bytes = BM * BK * 2 + (((uint32_t)bn * BK * 2 + 1023u) & ~1023u);
-  int stages = (int)(200 * 1024 / stage_bytes);
+  const size_t stg_bytes = (size_t)kTnEpiWarps * 32 * kStgLd * 4;
+  int stages = (int)((226 * 1024 - 1024 - 128 - stg_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 64 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 64 + stg_bytes + 1024;
   CUtensorMap ma, mb;
   int rc = make_map(&ma, a, (uint64_t)p.k, (uint64_t)p.m, (uint64_t)lda, BK, BM, "A operand");
   if (rc) return rc;

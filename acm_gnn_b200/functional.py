@@ -68,7 +68,7 @@ def tc_available() -> bool:
 def reorder_enabled(cfg: LayerConfig) -> bool:
     r = cfg.reorder
     if r == "env":
-        r = os.environ.get("ACMB200_REORDER", "off").lower()
+        r = os.environ.get("ACMB200_REORDER", "auto").lower()
     if r in ("auto", "1", "on"):
         return True
     if r in ("off", "0"):

@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--torch-loss", action="store_true",
                     help="use the reference's torch glue (log_softmax + index + nll_loss) instead of the fused loss kernel")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0 = leave default)")
-    ap.add_argument("--reorder", default=os.environ.get("ACMB200_REORDER", "off"), choices=["off", "auto"],
+    ap.add_argument("--reorder", default=os.environ.get("ACMB200_REORDER", "auto"), choices=["off", "auto"],
                     help="aggregate-first order A(XW)=(AX)W for layers whose input needs no gradient (SURVEY 8f rank 4)")
     return ap.parse_args()
 
@@ -369,6 +369,47 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms / cnt, "launches_timed": cnt}
     breakdown = {k: round(v[1] / args.steps, 4) for k, v in sorted(summ.items())}
 
+    # ---- the north-star kernel: fused SpMM + attention + mix at hidden=256, transform-first order.
+    # With --reorder auto layer 0 runs aggregate-first, so the fused gather kernel of layer 0 is timed here in a
+    # short separate pass of full train steps in the transform-first order (same graph, inputs, parameters).
+    north = None
+    if key_agg in summ:
+        os.environ["ACMB200_REORDER"] = "off"
+        k_ns = max(2, min(3, args.steps))
+        step(x, labels)
+        barrier()
+        t_ns = _lib.KernelTimer()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.set_timer(t_ns)
+        a.record()
+        for _ in range(k_ns):
+            step(x, labels)
+        b.record()
+        _lib.set_timer(None)
+        barrier()
+        os.environ["ACMB200_REORDER"] = args.reorder
+        ms_ns = torch.tensor([a.elapsed_time(b) / k_ns], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms_ns, op=dist.ReduceOp.MAX)
+        s_ns = t_ns.summary()
+        kf = f"acm_spmm_mix_fwd:{fp0}"
+        if kf in s_ns:
+            cnt, ms = s_ns[kf]
+            ab = nnz_loc * (2 * fp0 * s_el + 4) + n_loc * (fp0 * s_el + hid * 4 + 8) + n_loc * (2 * fp0 * s_el + 12)
+            ach = ab / (ms / cnt * 1e-3) / 1e9
+            tr = None
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{kf}:N{args.nodes}:E{args.edges}:{args.dtype}:w{world}")
+            except Exception:
+                pass
+            north = {"order": "transform-first: [HL|HH|HI] = X Wcat, then fused SpMM+attention+mix (north-star kernel)",
+                     "ms_per_step": float(ms_ns.item()), "value": nnz_global / (float(ms_ns.item()) * 1e-3), "unit": UNIT,
+                     "steps": k_ns,
+                     "roofline": {"bound": "hbm", "kernel": "spmm_mix_fwd_kernel (fused aggregation+attention+mix, layer 0)",
+                                  "achieved": ach, "peak": roof["peak"] if roof else None, "unit": "GB/s",
+                                  "frac": ach / roof["peak"] if roof else None, "traffic": tr,
+                                  "algorithmic_bytes_per_launch": ab, "avg_launch_ms": ms / cnt, "launches_timed": cnt}}
+
     # ---- end to end through the public module API with HOST buffers ---------------------------
     e2e = None
     if not args.no_e2e:
@@ -439,7 +480,8 @@ def run_ours(args):
             "config": workload_config(args, world),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches,
             "nnz": nnz_global, "peak_mem_gb": round(peak_mem, 2), "loss": final_loss,
-            "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first (layer 0)" if key_agg in summ else "transform-first (north-star fused SpMM+mix)",
+            "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first in layer 0 (A(XW)=(AX)W, SURVEY 8f rank 4), transform-first fused SpMM+mix in layer 1" if key_agg in summ else "transform-first (north-star fused SpMM+mix) in both layers",
+            "north_star_order": north,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
