@@ -12,6 +12,7 @@ import torch.nn.functional as F
 from torch.nn.parameter import Parameter
 
 from . import layers as _layers_pt
+from .functional import StagedInput
 from . import layers_geometric as _layers_geo
 
 
@@ -44,10 +45,18 @@ class GCN(nn.Module):
         self.skip_identity_relu = True
 
     def forward(self, x, adj_low, adj_high, adj_low_unnormalized):
-        x = F.dropout(x, self.dropout, training=self.training)
+        if isinstance(x, StagedInput):
+            # pre-staged input features (functional.stage_input): only meaningful when the input
+            # dropout is the identity, otherwise the features change every step
+            if self.training and self.dropout > 0:
+                raise ValueError("a StagedInput cannot be combined with input dropout > 0")
+            x_f32 = x.x
+        else:
+            x = F.dropout(x, self.dropout, training=self.training)
+            x_f32 = x
         xX = None
         if self.model_type == "acmgcnpp":
-            xX = F.dropout(F.relu(self.mlpX(x, input_tensor=True)), self.dropout, training=self.training)
+            xX = F.dropout(F.relu(self.mlpX(x_f32, input_tensor=True)), self.dropout, training=self.training)
         fea1 = self.gcns[0](x, adj_low, adj_high, adj_low_unnormalized)
         if not (self.skip_identity_relu and not self.gcns[0].variant):
             fea1 = F.relu(fea1)

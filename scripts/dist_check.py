@@ -23,7 +23,8 @@ def main():
     from acm_gnn_b200.functional import nll_log_softmax
     L.device = dev
     ok_all = True
-    for mode, variant, n in (("fp32", False, 5003), ("bf16", False, 5003), ("fp32", True, 4096)):
+    for mode, variant, n, staged in (("fp32", False, 5003, False), ("bf16", False, 5003, False), ("fp32", True, 4096, False),
+                                     ("fp32", False, 5003, True), ("bf16", False, 4100, True)):
         os.environ["ACMB200_DTYPE"] = mode
         fin, hid, ncls = 48, 64, 7
         g = torch.Generator(device=dev); g.manual_seed(5)
@@ -51,7 +52,10 @@ def main():
         part = RowPartition(n)
         m2 = attach(build(), part)
         opl = op.partition(part.r0, part.r1)
-        out2 = m2(x[part.r0:part.r1].contiguous(), opl, None, None)
+        x_loc = x[part.r0:part.r1].contiguous()
+        if staged:
+            x_loc = A.stage_input(x_loc, mode, part)
+        out2 = m2(x_loc, opl, None, None)
         nll_log_softmax(out2, labels[part.r0:part.r1].contiguous(), mask[part.r0:part.r1].contiguous(), n_train=ntr).backward()
         torch.cuda.synchronize()
         tol = 2e-5 if mode == "fp32" else 3e-2
@@ -66,7 +70,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         ok_all = ok_all and bool(t.item())
         if rank == 0:
-            print(f"dist_check world={world} mode={mode} variant={variant} n={n}: out rel.err {e_out:.2e}, worst grad rel.fro {worst:.2e} -> {'OK' if t.item() else 'FAIL'}", flush=True)
+            print(f"dist_check world={world} mode={mode} variant={variant} staged={staged} n={n}: out rel.err {e_out:.2e}, worst grad rel.fro {worst:.2e} -> {'OK' if t.item() else 'FAIL'}", flush=True)
     if rank == 0:
         print("DIST_CHECK", "PASS" if ok_all else "FAIL", flush=True)
     dist.destroy_process_group()

@@ -359,3 +359,34 @@ def test_gcn_golden_with_aggregate_first(name, monkeypatch):
         if k in ("fea_param", "xX_param") or ".bns." in k or ref_grads[k].size == 0:
             continue
         _close_grad(p_.grad, ref_grads[k], "fp32", "grad " + k)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_staged_input_is_equivalent(mode):
+    """functional.stage_input (features pre-staged in the kernel layout) gives bit-identical
+    results to passing the raw fp32 tensor, in both orders."""
+    import acm_gnn_b200 as A
+    os.environ["ACMB200_DTYPE"] = mode
+    g = Golden("gcn_pt_acmgcn_v0")
+    model = _cuda_model(g, mode)
+    op = A.AcmOperator.from_edges(torch.from_numpy(g.row).cuda(), torch.from_numpy(g.col).cuda(), g.n)
+    x = g.x.cuda()
+    for order in ("auto", "off"):
+        os.environ["ACMB200_REORDER"] = order
+        try:
+            outs, grads = [], []
+            for xin in (x, A.stage_input(x, mode)):
+                model.zero_grad(set_to_none=True)
+                out = model(xin, op, None, None)
+                out.square().sum().backward()
+                outs.append(out.detach().clone())
+                grads.append(model.gcns[0].weight_high.grad.detach().clone())
+            assert torch.equal(outs[0], outs[1])
+            if mode == "fp32":
+                np.testing.assert_allclose(grads[0].cpu().numpy(), grads[1].cpu().numpy(), rtol=1e-4, atol=1e-7)  # split-K atomics reorder sums
+        finally:
+            os.environ.pop("ACMB200_REORDER", None)
+    model.train()
+    model.dropout = 0.5
+    with pytest.raises(ValueError):
+        model(A.stage_input(x, mode), op, None, None)
