@@ -100,6 +100,28 @@ __device__ __forceinline__ float group_sum(float v) {
 
 __device__ __forceinline__ float sigmoidf_acc(float z) { return 1.0f / (1.0f + expf(-z)); }
 
+// ---- long rows --------------------------------------------------------------------------------
+// Rows with more than kLongRow stored edges are aggregated by a separate segment-parallel pass
+// (spmm_long_rows_kernel) into an fp32 side buffer; the row kernels then read the finished sums
+// instead of walking thousands of edges with one lane group (degree skew: Squirrel 1904,
+// twitch-gamers ~35k).  long_rows is sorted ascending.
+constexpr int kLongRow = 256;
+
+struct LongRows {
+  const int32_t* rows;   // [n_long] local row ids, ascending (nullptr: none)
+  const float* acc;      // [n_long, width] finished fp32 sums
+  int n_long;
+};
+
+__device__ __forceinline__ int find_long_row(const LongRows& lr, int64_t row) {
+  int lo = 0, hi = lr.n_long;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (lr.rows[mid] < row) lo = mid + 1; else hi = mid;
+  }
+  return lo;  // caller guarantees presence
+}
+
 // layout of the attention parameter pack (see acm_b200.h)
 __host__ __device__ __forceinline__ int pack_off_a(int fp, int k) { return k * fp; }
 __host__ __device__ __forceinline__ int pack_off_avec(int fp) { return 4 * fp; }

@@ -31,6 +31,7 @@ struct FwdParams {
   void* o_save;
   float* att;
   float* sig;
+  LongRows lr;
 };
 
 constexpr int kFwdWarps = 8;
@@ -87,6 +88,17 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
   float accL[8], accH[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) accL[t] = accH[t] = 0.f;
+
+  if (p.lr.rows != nullptr && e1 - e > kLongRow) {
+    // long row: sums were produced by the segment-parallel pass
+    const float* a = p.lr.acc + (int64_t)find_long_row(p.lr, row) * TW + gl * 8;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      accL[t] = a[t];
+      accH[t] = a[FP + t];
+    }
+    e = e1;
+  }
 
   // ---- gather loop: kUnroll independent neighbour rows in flight per lane ----------------
   for (; e + kUnroll <= e1; e += kUnroll) {
@@ -281,7 +293,8 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
                                 const int64_t* rowptr, const int32_t* col, const float* val, const float* rowscale,
                                 const void* table, const void* h_i, const void* o_s,
                                 const float* pack, int k_channels, int ln_live, int variant, float out_scale,
-                                float* y, int64_t ldy, void* o_save, float* att, float* sig, void* stream) {
+                                float* y, int64_t ldy, void* o_save, float* att, float* sig,
+                                const int32_t* long_rows, int n_long, const float* long_acc, void* stream) {
   using namespace acm;
   ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_mix_fwd: bad dtype %d", dtype);
   ACM_CHECK_ARG(k_channels == 3 || k_channels == 4, "spmm_mix_fwd: k_channels must be 3 or 4");
@@ -295,6 +308,8 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
   p.variant = variant; p.f = f; p.out_scale = out_scale; p.y = y; p.ldy = ldy; p.o_save = o_save;
   p.att = att; p.sig = sig;
   p.pre_agg = (rowptr == nullptr);
+  p.lr.rows = n_long > 0 ? long_rows : nullptr; p.lr.acc = long_acc; p.lr.n_long = n_long;
+  ACM_CHECK_ARG(n_long == 0 || (long_rows && long_acc), "spmm_mix_fwd: long rows need long_rows and long_acc");
   p.vec_y = (f % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int mode = (k_channels == 4 || ln_live) ? 1 : 0;

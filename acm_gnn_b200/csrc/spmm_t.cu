@@ -18,7 +18,7 @@ template <typename T, int FP>
 __global__ void __launch_bounds__(kTWarps * 32)
 spmm_t_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
               const float* __restrict__ val, const T* __restrict__ table, const T* __restrict__ ptab,
-              T* __restrict__ dh_all) {
+              T* __restrict__ dh_all, const LongRows lr) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
   constexpr int TW = 2 * FP;
@@ -32,6 +32,15 @@ spmm_t_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, 
   float accL[8], accH[8];
 #pragma unroll
   for (int t = 0; t < 8; ++t) accL[t] = accH[t] = 0.f;
+  if (lr.rows != nullptr && e1 - e > kLongRow) {
+    const float* a = lr.acc + (int64_t)find_long_row(lr, row) * TW + gl * 8;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      accL[t] = a[t];
+      accH[t] = a[FP + t];
+    }
+    e = e1;
+  }
   for (; e + kTUnroll <= e1; e += kTUnroll) {
     int32_t c[kTUnroll];
     float w[kTUnroll];
@@ -164,7 +173,7 @@ template <typename T, int FP>
 __global__ void __launch_bounds__(kTWarps * 32)
 spmm_agg_first_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                       const float* __restrict__ val, const T* __restrict__ table, T* __restrict__ z_out,
-                      T* __restrict__ d_out) {
+                      T* __restrict__ d_out, const LongRows lr) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -178,6 +187,12 @@ spmm_agg_first_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ 
 #pragma unroll
   for (int t = 0; t < 8; ++t) acc[t] = 0.f;
   constexpr int U = 8;  // narrower rows than the [HL|HH] table: keep the same bytes in flight
+  if (lr.rows != nullptr && e1 - e > kLongRow) {
+    const float* a = lr.acc + (int64_t)find_long_row(lr, row) * FP + gl * 8;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = a[t];
+    e = e1;
+  }
   for (; e + U <= e1; e += U) {
     int32_t c[U];
     float w[U];
@@ -219,12 +234,108 @@ spmm_agg_first_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ 
   Slice8<T>::store(d_out + row * FP + gl * 8, d);
 }
 
+// Segment-parallel aggregation of the long rows: one lane group per segment of <= kLongRow
+// edges, partial sums added atomically into acc[long_index, :] (fp32, zeroed by the caller).
+// HALVES = 2: table rows are [L | H] pairs of FP features (row width 2*FP); 1: single FP-wide rows.
+template <typename T, int FP, int HALVES>
+__global__ void __launch_bounds__(kTWarps * 32)
+spmm_long_rows_kernel(int64_t n_seg, const int32_t* __restrict__ seg_long, const int64_t* __restrict__ seg_e0,
+                      const int64_t* __restrict__ seg_e1, const int32_t* __restrict__ col,
+                      const float* __restrict__ val, const T* __restrict__ table, float* __restrict__ acc_out) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPW = 32 / LANES;
+  constexpr int TW = HALVES * FP;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LANES, gl = lane % LANES;
+  const int64_t seg = ((int64_t)blockIdx.x * kTWarps + warp) * RPW + sub;
+  if (seg >= n_seg) return;
+  int64_t e = seg_e0[seg];
+  const int64_t e1 = seg_e1[seg];
+  const T* tab = table + gl * 8;
+  float acc[HALVES][8];
+#pragma unroll
+  for (int h = 0; h < HALVES; ++h)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[h][t] = 0.f;
+  for (; e + kTUnroll <= e1; e += kTUnroll) {
+    int32_t c[kTUnroll];
+    float w[kTUnroll];
+#pragma unroll
+    for (int u = 0; u < kTUnroll; ++u) {
+      c[u] = __ldg(col + e + u);
+      w[u] = val ? __ldg(val + e + u) : 1.f;
+    }
+    Slice8<T> v[kTUnroll][HALVES];
+#pragma unroll
+    for (int u = 0; u < kTUnroll; ++u)
+#pragma unroll
+      for (int h = 0; h < HALVES; ++h) v[u][h].load(tab + (int64_t)c[u] * TW + h * FP);
+#pragma unroll
+    for (int u = 0; u < kTUnroll; ++u)
+#pragma unroll
+      for (int h = 0; h < HALVES; ++h) {
+        float f[8];
+        v[u][h].to_float(f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[h][t] = fmaf(w[u], f[t], acc[h][t]);
+      }
+  }
+  for (; e < e1; ++e) {
+    const int32_t c = __ldg(col + e);
+    const float w = val ? __ldg(val + e) : 1.f;
+#pragma unroll
+    for (int h = 0; h < HALVES; ++h) {
+      Slice8<T> v;
+      v.load(tab + (int64_t)c * TW + h * FP);
+      float f[8];
+      v.to_float(f);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[h][t] = fmaf(w, f[t], acc[h][t]);
+    }
+  }
+  float* o = acc_out + (int64_t)seg_long[seg] * TW + gl * 8;
+#pragma unroll
+  for (int h = 0; h < HALVES; ++h)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) atomicAdd(o + h * FP + t, acc[h][t]);
+}
+
 }  // namespace acm
+
+extern "C" int acm_spmm_long_rows(int dtype, int fp, int halves, int64_t n_seg, const int32_t* seg_long,
+                                  const int64_t* seg_e0, const int64_t* seg_e1, const int32_t* col, const float* val,
+                                  const void* table, float* acc_out, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_long_rows: bad dtype %d", dtype);
+  ACM_CHECK_ARG(halves == 1 || halves == 2, "spmm_long_rows: halves must be 1 or 2");
+  ACM_CHECK_ARG(seg_long && seg_e0 && seg_e1 && col && table && acc_out, "spmm_long_rows: null pointer");
+  if (n_seg == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define ACM_L_LAUNCH(TT, HH)                                                                    \
+  ACM_DISPATCH_FP(fp, {                                                                         \
+    constexpr int RPB = (32 / (FP / 8)) * kTWarps;                                              \
+    const int64_t blocks = (n_seg + RPB - 1) / RPB;                                             \
+    ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_long_rows: too many segments");                   \
+    spmm_long_rows_kernel<TT, FP, HH><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(               \
+        n_seg, seg_long, seg_e0, seg_e1, col, val, (const TT*)table, acc_out);                  \
+  })
+  if (dtype == ACM_BF16) {
+    if (halves == 2) { ACM_L_LAUNCH(__nv_bfloat16, 2); } else { ACM_L_LAUNCH(__nv_bfloat16, 1); }
+  } else {
+    if (halves == 2) { ACM_L_LAUNCH(float, 2); } else { ACM_L_LAUNCH(float, 1); }
+  }
+#undef ACM_L_LAUNCH
+  ACM_LAUNCH_CHECK("spmm_long_rows");
+  return 0;
+}
 
 extern "C" int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row0,
                                   const int64_t* rowptr, const int32_t* col, const float* val,
-                                  const void* table, void* z_out, void* d_out, void* stream) {
+                                  const void* table, void* z_out, void* d_out,
+                                  const int32_t* long_rows, int n_long, const float* long_acc, void* stream) {
   using namespace acm;
+  LongRows lr{n_long > 0 ? long_rows : nullptr, long_acc, n_long};
+  ACM_CHECK_ARG(n_long == 0 || (long_rows && long_acc), "spmm_agg_first: long rows need long_rows and long_acc");
   ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_agg_first: bad dtype %d", dtype);
   ACM_CHECK_ARG(rowptr && col && table && z_out && d_out, "spmm_agg_first: null pointer");
   if (n_rows == 0) return 0;
@@ -235,7 +346,7 @@ extern "C" int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row
     const int64_t blocks = (n_rows + RPB - 1) / RPB;                                              \
     ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_agg_first: too many rows");                         \
     spmm_agg_first_kernel<TT, FP><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                     \
-        n_rows, row0, rowptr, col, val, (const TT*)table, (TT*)z_out, (TT*)d_out);                \
+        n_rows, row0, rowptr, col, val, (const TT*)table, (TT*)z_out, (TT*)d_out, lr);            \
   })
   if (dtype == ACM_BF16) { ACM_A_LAUNCH(__nv_bfloat16); } else { ACM_A_LAUNCH(float); }
 #undef ACM_A_LAUNCH
@@ -245,8 +356,11 @@ extern "C" int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row
 
 extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
                               const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
-                              const void* t_table, const void* p_table, void* dh_all, void* stream) {
+                              const void* t_table, const void* p_table, void* dh_all,
+                              const int32_t* long_rows, int n_long, const float* long_acc, void* stream) {
   using namespace acm;
+  LongRows lr{n_long > 0 ? long_rows : nullptr, long_acc, n_long};
+  ACM_CHECK_ARG(n_long == 0 || (long_rows && long_acc), "spmm_t_bwd: long rows need long_rows and long_acc");
   ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_t_bwd: bad dtype %d", dtype);
   ACM_CHECK_ARG(rowptr_t && col_t && t_table && dh_all, "spmm_t_bwd: null pointer");
   if (n_rows == 0) return 0;
@@ -257,7 +371,7 @@ extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
     const int64_t blocks = (n_rows + RPB - 1) / RPB;                                               \
     ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_t_bwd: too many rows");                              \
     spmm_t_kernel<TT, FP><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                              \
-        n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all); \
+        n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all, lr); \
   })
   if (dtype == ACM_BF16) { ACM_T_LAUNCH(__nv_bfloat16); } else { ACM_T_LAUNCH(float); }
 #undef ACM_T_LAUNCH

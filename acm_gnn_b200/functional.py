@@ -119,6 +119,21 @@ def build_wcat(fp, f, ws, dtype):
     return wcat.to(dtype)
 
 
+def _long_pass(csr, transposed, table, fp, halves, cdt, st):
+    """Segment-parallel aggregation of the long rows of ``csr`` (degree skew).  Returns the
+    (long_rows_ptr, n_long, acc_ptr, keepalive) arguments of the row kernels."""
+    lr = csr.long_rows(transposed)
+    if lr is None:
+        return 0, 0, 0, None
+    rows, seg_long, e0, e1 = lr
+    col = csr.col_t if transposed else csr.col
+    val = csr.val_t if transposed else csr.val
+    acc = torch.zeros(rows.numel(), halves * fp, dtype=torch.float32, device=rows.device)
+    _lib.call("acm_spmm_long_rows", cdt, fp, halves, seg_long.numel(), seg_long.data_ptr(), e0.data_ptr(), e1.data_ptr(),
+              col.data_ptr(), val.data_ptr(), table.data_ptr(), acc.data_ptr(), st)
+    return rows.data_ptr(), int(rows.numel()), acc.data_ptr(), (rows, acc)
+
+
 class StagedInput:
     """Layer-0 input features already resident in HBM in the layout the kernels consume: the
     storage-dtype copy padded to the power-of-two width (``xs`` [n_local, ldx]) and, under a row
@@ -208,9 +223,10 @@ class AcmLayerFunction(torch.autograd.Function):
                 x_all = xs if cfg.dist is None else cfg.dist.all_gather_rows(xs)
             z = torch.empty(n, ldx, dtype=tdt, device=dev)
             d = torch.empty(n, ldx, dtype=tdt, device=dev)
+            lr = _long_pass(op.low, False, x_all, ldx, 1, cdt, st)
             _lib.call("acm_spmm_agg_first", cdt, ldx, n, op.row0, op.low.rowptr.data_ptr(), op.low.col.data_ptr(),
-                      op.low.val.data_ptr(), x_all.data_ptr(), z.data_ptr(), d.data_ptr(), st, tag=ldx)
-            del x_all
+                      op.low.val.data_ptr(), x_all.data_ptr(), z.data_ptr(), d.data_ptr(), lr[0], lr[1], lr[2], st, tag=ldx)
+            del x_all, lr
             wp = torch.zeros(ldx, 3 * fp, dtype=tdt, device=dev)   # rows fin..ldx are zero
             wp[:fin] = wcat
             wt = wp.t().contiguous() if impl == _lib.GEMM_TCGEN05 else None  # [3fp, ldx], K-major
@@ -222,6 +238,7 @@ class AcmLayerFunction(torch.autograd.Function):
             del wp, wt
             table, csr = h_lh, (0, 0, 0)      # pre-aggregated: only the epilogue of the fused kernel runs
             row0 = 0
+            lr = (0, 0, 0, None)
         else:
             # staging copy of the layer input in the storage dtype (row stride padded to 8)
             if staged is not None:
@@ -242,6 +259,7 @@ class AcmLayerFunction(torch.autograd.Function):
             table = h_lh if cfg.dist is None else cfg.dist.all_gather_rows(h_lh)
             csr = (op.low.rowptr.data_ptr(), op.low.col.data_ptr(), op.low.val.data_ptr())
             row0 = op.row0
+            lr = _long_pass(op.low, False, table, fp, 2, cdt, st)
 
         o_s = None
         if K == 4:
@@ -265,7 +283,8 @@ class AcmLayerFunction(torch.autograd.Function):
         _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, row0, csr[0], csr[1], csr[2], 0,
                   table.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s), pack.data_ptr(),
                   K, int(cfg.ln_live), int(cfg.variant), float(cfg.out_scale),
-                  y.data_ptr(), f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig), st, tag=fp)
+                  y.data_ptr(), f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig), lr[0], lr[1], lr[2], st, tag=fp)
+        del lr
 
         ctx.mark_non_differentiable(att)
         if need_grad:
@@ -309,9 +328,11 @@ class AcmLayerFunction(torch.autograd.Function):
                           dwcat[:, k * fp:].data_ptr(), 3 * fp, n, fin, fp, st, tag=fp)
         else:
             t_table = t_lh if cfg.dist is None else cfg.dist.all_gather_rows(t_lh)
+            lr = _long_pass(op.low, True, t_table, fp, 2, cdt, st)
             _lib.call("acm_spmm_t_bwd", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
-                      op.low.val_t.data_ptr(), t_table.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(), st, tag=fp)
-            del t_table
+                      op.low.val_t.data_ptr(), t_table.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(),
+                      lr[0], lr[1], lr[2], st, tag=fp)
+            del t_table, lr
             _lib.call("acm_gemm_bwd_dw", impl, cdt, xs.data_ptr(), ldx, dh_all.data_ptr(), dwcat.data_ptr(), n, fin, fp, st, tag=fp)
             if ctx.x_needs_grad:
                 dx = torch.empty(n, fin, dtype=torch.float32, device=dev)

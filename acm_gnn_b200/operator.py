@@ -80,6 +80,32 @@ class CsrMatrix:
         self.rowptr_t, self.col_t, self.val_t = t.rowptr, t.col, t.val
         return self
 
+    # -- degree skew: segment tables of the long rows (see csrc/acm_common.cuh kLongRow) ---------
+    LONG_ROW = 256
+
+    def long_rows(self, transposed=False):
+        """(rows int32 [L] ascending, seg_long int32 [S], seg_e0 int64 [S], seg_e1 int64 [S]) of
+        the rows with more than LONG_ROW stored edges, or None when there are none."""
+        attr = "_long_t" if transposed else "_long"
+        if hasattr(self, attr):
+            return getattr(self, attr)
+        rowptr = self.rowptr_t if transposed else self.rowptr
+        deg = rowptr[1:] - rowptr[:-1]
+        long = torch.nonzero(deg > self.LONG_ROW).squeeze(1)
+        res = None
+        if long.numel() > 0:
+            t = self.LONG_ROW
+            nseg = (deg[long] + t - 1) // t
+            seg_long = torch.repeat_interleave(torch.arange(long.numel(), device=long.device), nseg)
+            first = torch.cumsum(nseg, 0) - nseg
+            within = torch.arange(seg_long.numel(), device=long.device) - first[seg_long]
+            e0 = rowptr[long][seg_long] + within * t
+            e1 = torch.minimum(e0 + t, rowptr[long + 1][seg_long])
+            res = (long.to(torch.int32).contiguous(), seg_long.to(torch.int32).contiguous(),
+                   e0.contiguous(), e1.contiguous())
+        setattr(self, attr, res)
+        return res
+
     def rows(self):
         return torch.repeat_interleave(torch.arange(self.n_rows, device=self.device, dtype=torch.int64),
                                        self.rowptr[1:] - self.rowptr[:-1])

@@ -111,7 +111,18 @@ int acm_gemm_atb(int impl, int dtype, const void* a, int64_t lda, const void* b,
  * of the INPUT row per stored edge instead of the 2*out_features wide [HL|HH] row. */
 int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row0,
                        const int64_t* rowptr, const int32_t* col, const float* val,
-                       const void* table, void* z_out, void* d_out, void* stream);
+                       const void* table, void* z_out, void* d_out,
+                       const int32_t* long_rows, int n_long, const float* long_acc, void* stream);
+
+/* Degree skew.  Rows with more than 256 stored edges ("long rows": local ids in long_rows,
+ * ascending) are aggregated by this segment-parallel pass -- one lane group per segment
+ * [seg_e0, seg_e1) of <= 256 edges, seg_long = index of the segment's row in long_rows --
+ * into acc_out [n_long, halves*fp] (fp32, zeroed by the caller, atomically accumulated).  The
+ * row kernels above take (long_rows, n_long, long_acc) and read these sums instead of walking
+ * the edges.  halves = 2 for the [L|H] tables (row width 2*fp), 1 for single fp-wide rows. */
+int acm_spmm_long_rows(int dtype, int fp, int halves, int64_t n_seg, const int32_t* seg_long,
+                       const int64_t* seg_e0, const int64_t* seg_e1, const int32_t* col, const float* val,
+                       const void* table, float* acc_out, void* stream);
 
 /* ---- fused aggregation + channel attention + mix (THE hot kernel) -------------------
  * layers.py:176-204 + attention3/attention4 (94-152) in one launch:
@@ -130,7 +141,8 @@ int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
                      const int64_t* rowptr, const int32_t* col, const float* val, const float* rowscale,
                      const void* table, const void* h_i, const void* o_s,
                      const float* pack, int k_channels, int ln_live, int variant, float out_scale,
-                     float* y, int64_t ldy, void* o_save, float* att, float* sig, void* stream);
+                     float* y, int64_t ldy, void* o_save, float* att, float* sig,
+                     const int32_t* long_rows, int n_long, const float* long_acc, void* stream);
 
 /* Row-local backward of the attention/mix/relu part (autograd of layers.py:94-152,
  * 185-204).  g = dL/dY [n_rows, f].  Writes t_lh [n_rows, 2*fp] = [dS_L | dS_H] (the table
@@ -150,7 +162,8 @@ int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
  * table; the result is masked by p > 0 (relu before aggregation). */
 int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
                    const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
-                   const void* t_table, const void* p_table, void* dh_all, void* stream);
+                   const void* t_table, const void* p_table, void* dh_all,
+                   const int32_t* long_rows, int n_long, const float* long_acc, void* stream);
 
 /* Plain single-table aggregation out = [relu](A . table), table T [*, fp]; used for the
  * structure channel relu(mm(adj_low_unnormalized, struc_low)) (layers.py:207-209) and its
