@@ -73,7 +73,12 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
   const int warp = threadIdx.x >> 5;
   const int sub = lane / LANES;
   const int gl = lane % LANES;
-  const int64_t row = ((int64_t)blockIdx.x * kFwdWarps + warp) * RPW + sub;
+  // one pass per block in gather mode (the hardware block scheduler balances the degrees);
+  // grid-stride in the pre-aggregated mode, where a block's rows are too little work to
+  // amortise the parameter-pack load above
+  const int64_t n_blocks = (p.n_rows + (int64_t)kFwdWarps * RPW - 1) / ((int64_t)kFwdWarps * RPW);
+  for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
+  const int64_t row = (rb * kFwdWarps + warp) * RPW + sub;
   const bool valid = row < p.n_rows;
 
   int64_t e = 0, e1 = 0;
@@ -241,7 +246,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) a[k] *= rden;
 
-  if (!valid) return;
+  if (!valid) continue;
 
   float yv[8];
 #pragma unroll
@@ -272,14 +277,16 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
       if (p.sig) p.sig[row * K + k] = s[k];
     }
   }
+  }  // row-block loop
 }
 
 template <typename T, int FP, int MODE>
 static int launch_fwd(const FwdParams& p, cudaStream_t st) {
   constexpr int LANES = FP / 8;
   constexpr int RPB = (32 / LANES) * kFwdWarps;
-  const int64_t blocks = (p.n_rows + RPB - 1) / RPB;
+  int64_t blocks = (p.n_rows + RPB - 1) / RPB;
   if (blocks == 0) return 0;
+  if (p.pre_agg && blocks > 148 * 16) blocks = 148 * 16;
   ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_mix_fwd: too many rows for one launch");
   const size_t smem = sizeof(float) * ((MODE ? 4 : 3) * FP + 16 + (MODE ? 4 * FP + 8 : 0));
   spmm_mix_fwd_kernel<T, FP, MODE><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);

@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--torch-loss", action="store_true",
                     help="use the reference's torch glue (log_softmax + index + nll_loss) instead of the fused loss kernel")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0 = leave default)")
+    ap.add_argument("--skew", type=float, default=0.0,
+                    help="degree-skewed variant of the synthetic graph (SURVEY 8d): destination = N*u^skew, u~U(0,1), "
+                         "ids randomly permuted; 0 = uniform endpoints (the headline workload)")
     ap.add_argument("--no-stage-input", action="store_true",
                     help="pass the raw fp32 feature tensor to the model every step (cast + all-gather inside the timed region) "
                          "instead of features staged once in the kernel layout")
@@ -62,14 +65,21 @@ def parse_args():
 # synthetic inputs
 # ----------------------------------------------------------------------------------------
 
-def synthetic_graph_gpu(n, e_directed, device, seed=0):
+def synthetic_graph_gpu(n, e_directed, device, seed=0, skew=0.0):
     """Uniform random undirected pairs, self loops dropped, symmetrised, duplicates coalesced."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     eu = e_directed // 2
     src = torch.randint(0, n, (eu,), generator=g, device=device, dtype=torch.int64)
-    dst = torch.randint(0, n, (eu,), generator=g, device=device, dtype=torch.int64)
+    if skew > 0:
+        u = torch.rand(eu, generator=g, device=device, dtype=torch.float64)
+        dst = torch.clamp((n * u.pow(skew)).to(torch.int64), max=n - 1)
+        perm = torch.randperm(n, generator=g, device=device)
+        dst = perm[dst]
+        del u, perm
+    else:
+        dst = torch.randint(0, n, (eu,), generator=g, device=device, dtype=torch.int64)
     keep = src != dst
     src, dst = src[keep], dst[keep]
     key = torch.unique(torch.cat([src * n + dst, dst * n + src]))
@@ -191,7 +201,7 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": f"synthetic uniform random graph N={args.nodes} E={args.edges} (+N self loops), Fin={args.fin} "
                         f"hidden={args.hidden} classes={args.nclass}, 2-layer acmgcn variant 0 dropout 0 (SURVEY 8d cfg 5)",
-            "nodes": args.nodes, "edges": args.edges, "fin": args.fin, "hidden": args.hidden, "nclass": args.nclass,
+            "skew": args.skew, "nodes": args.nodes, "edges": args.edges, "fin": args.fin, "hidden": args.hidden, "nclass": args.nclass,
             "step": "forward + log_softmax/NLL (" + ("torch glue" if args.torch_loss else "fused acm_nll_log_softmax") + ") + backward + Adam.step",
             "partition": f"1-D row partition over {world} GPU(s), NCCL all-gather of the operand table" if world > 1 else "single GPU",
             "input_staging": "raw fp32 features every step" if args.no_stage_input else "features staged once in the kernel layout (bf16, padded, all-gathered across ranks) before the timed region; e2e starts from host fp32 buffers every step",
@@ -235,10 +245,13 @@ def run_ours(args):
         raise SystemExit(f"workload needs ~{est/1e9:.0f} GB, only {free/1e9:.0f} GB free: refusing to risk an OOM")
 
     # ---- inputs, resident in HBM before the timed region -------------------------------------
-    row, col = synthetic_graph_gpu(n, args.edges, dev, seed=0)
+    row, col = synthetic_graph_gpu(n, args.edges, dev, seed=0, skew=args.skew)
     op_full = A.AcmOperator.from_edges(row, col, n, "pytorch")
     del row, col
     nnz_global = op_full.nnz
+    max_deg = int((op_full.low.rowptr[1:] - op_full.low.rowptr[:-1]).max().item())
+    _lr = op_full.low.long_rows()
+    n_long_rows = 0 if _lr is None else int(_lr[0].numel())
     part = None
     if world > 1:
         part = RowPartition(n)
@@ -493,7 +506,7 @@ def run_ours(args):
             "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(args, world),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches,
-            "nnz": nnz_global, "peak_mem_gb": round(peak_mem, 2), "loss": final_loss,
+            "nnz": nnz_global, "max_degree": max_deg, "long_rows": n_long_rows, "peak_mem_gb": round(peak_mem, 2), "loss": final_loss,
             "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first in layer 0 (A(XW)=(AX)W, SURVEY 8f rank 4), transform-first fused SpMM+mix in layer 1" if key_agg in summ else "transform-first (north-star fused SpMM+mix) in both layers",
             "north_star_order": north,
         }
