@@ -122,6 +122,20 @@ __device__ __forceinline__ int find_long_row(const LongRows& lr, int64_t row) {
   return lo;  // caller guarantees presence
 }
 
+// ---- fused exchange: push to peer memory --------------------------------------------------------
+// Under a 1-D row partition the operand table of an aggregation is needed on EVERY rank.  Instead
+// of writing the own rows locally and calling an all-gather afterwards, the producing kernel
+// (GEMM epilogue forward, mix_bwd backward) stores each finished row straight into all ranks'
+// tables through NVLink peer mappings (symmetric memory): the transfer overlaps the compute and
+// the all-gather disappears as a separate step.  tables[r] = base of rank r's [N_pad, width]
+// table; rows are written at global index row_off + local row.
+constexpr int kMaxPeers = 8;
+struct PeerTables {
+  void* tables[kMaxPeers];
+  int n;               // 0 = no push (single GPU / NCCL path)
+  int64_t row_off;
+};
+
 // layout of the attention parameter pack (see acm_b200.h)
 __host__ __device__ __forceinline__ int pack_off_a(int fp, int k) { return k * fp; }
 __host__ __device__ __forceinline__ int pack_off_avec(int fp) { return 4 * fp; }

@@ -9,7 +9,7 @@ namespace acm {
 
 // gemm_tc.cu
 int tc_gemm_fwd(const void* x, int64_t ldx, const void* wcat_t, void* h_lh, void* h_i, int64_t n, int64_t fin,
-                int64_t fp, int relu_lh, cudaStream_t st);
+                int64_t fp, int relu_lh, const PeerTables* peers, cudaStream_t st);
 int tc_gemm_dw(const void* x, int64_t ldx, const void* dh, float* dwcat, int64_t n, int64_t fin, int64_t fp,
                cudaStream_t st);
 int tc_gemm_dx(const void* dh, const void* wcat, float* dx, int64_t lddx, int64_t n, int64_t fin, int64_t fp,
@@ -77,7 +77,7 @@ extern "C" int acm_gemm_xw_fwd(int impl, int dtype, const void* x, int64_t ldx, 
   if (impl == ACM_GEMM_TCGEN05) {
     ACM_CHECK_ARG(dtype == ACM_BF16, "gemm_xw_fwd: the tcgen05 path computes in bf16; storage dtype must be bf16");
     ACM_CHECK_ARG(wcat_t, "gemm_xw_fwd: tcgen05 path needs wcat_t");
-    return tc_gemm_fwd(x, ldx, wcat_t, h_lh, h_i, n, fin, fp, relu_lh, st);
+    return tc_gemm_fwd(x, ldx, wcat_t, h_lh, h_i, n, fin, fp, relu_lh, nullptr, st);
   }
   ACM_CHECK_ARG(impl == ACM_GEMM_SIMT, "gemm_xw_fwd: unknown impl %d", impl);
   ACM_CHECK_ARG(wcat, "gemm_xw_fwd: SIMT path needs wcat");
@@ -135,4 +135,16 @@ extern "C" int acm_gemm_bwd_dx(int impl, int dtype, const void* dh, const void* 
   p.m = n; p.n = fin; p.k = 3 * fp;
   p.c_bf16 = 0; p.relu_cols = 0; p.atomic = 0;
   return gemm_simt(dtype, p, 1, st);
+}
+
+extern "C" int acm_gemm_xw_fwd_push(const void* x, int64_t ldx, const void* wcat_t, void* const* peer_tables, int n_peers,
+                                    int64_t row_off, void* h_i, int64_t n, int64_t fin, int64_t fp, int relu_lh,
+                                    void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(x && wcat_t && peer_tables && h_i, "gemm_xw_fwd_push: null pointer");
+  ACM_CHECK_ARG(n_peers >= 1 && n_peers <= kMaxPeers, "gemm_xw_fwd_push: 1 <= n_peers <= %d", kMaxPeers);
+  PeerTables pt{};
+  pt.n = n_peers; pt.row_off = row_off;
+  for (int r = 0; r < n_peers; ++r) pt.tables[r] = peer_tables[r];
+  return tc_gemm_fwd(x, ldx, wcat_t, nullptr, h_i, n, fin, fp, relu_lh, &pt, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -97,6 +97,8 @@ struct TnParams {
   int relu_cols;
   // MODE 1 (dX): fp32 output
   float* cf; int64_t ldcf; int vec_ok;
+  // MODE 0: optional push of the c0 part ([HL|HH] rows) into every rank's table (peer memory)
+  PeerTables peers;
 };
 
 constexpr int kStgLd = 36;                           // staging row stride in words (32 + 4 pad)
@@ -233,8 +235,20 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
             }
-            __nv_bfloat16* dst = (j < p.ncols0) ? p.c0 + row * p.ldc0 + j : p.c1 + row * p.ldc1 + (j - p.ncols0);
-            *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
+            const uint4 packed = pack_bf16x8(v);
+            if (j < p.ncols0) {
+              if (p.peers.n > 0) {
+                // fused all-gather: the finished row segment goes to every rank's table over NVLink
+                const int64_t off = (p.peers.row_off + row) * p.ldc0 + j;
+#pragma unroll 1
+                for (int r = 0; r < p.peers.n; ++r)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.peers.tables[r]) + off) = packed;
+              } else {
+                *reinterpret_cast<uint4*>(p.c0 + row * p.ldc0 + j) = packed;
+              }
+            } else {
+              *reinterpret_cast<uint4*>(p.c1 + row * p.ldc1 + (j - p.ncols0)) = packed;
+            }
           }
         } else {
           // 8 lanes x 16 B (4 fp32) per row, 4 rows per pass
@@ -468,8 +482,9 @@ static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, TnP
 }  // namespace tc
 
 int tc_gemm_fwd(const void* x, int64_t ldx, const void* wcat_t, void* h_lh, void* h_i, int64_t n, int64_t fin,
-                int64_t fp, int relu_lh, cudaStream_t st) {
+                int64_t fp, int relu_lh, const PeerTables* peers, cudaStream_t st) {
   tc::TnParams p{};
+  if (peers) p.peers = *peers;
   p.m = n; p.n = 3 * fp; p.k = fin;
   p.c0 = (__nv_bfloat16*)h_lh; p.ldc0 = 2 * fp; p.ncols0 = (int)(2 * fp);
   p.c1 = (__nv_bfloat16*)h_i; p.ldc1 = fp;

@@ -13,7 +13,8 @@ namespace acm {
 template <int CMAX>
 __global__ void __launch_bounds__(256)
 nll_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int c, const int64_t* __restrict__ labels,
-           const uint8_t* __restrict__ mask, float scale, float* __restrict__ loss, float* __restrict__ dx, int64_t lddx) {
+           const uint8_t* __restrict__ mask, float scale, float* __restrict__ loss, float* __restrict__ dx, int64_t lddx,
+           int vec, int vec_d) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float li = 0.f;
   if (i < n) {
@@ -22,11 +23,22 @@ nll_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int c, const int6
     const float* xr = x + i * ld;
     if (on) {
       float mx = -INFINITY;
+      if (vec) {  // c % 4 == 0, 16-byte aligned rows: 128-bit loads
 #pragma unroll
-      for (int j = 0; j < CMAX; ++j) {
-        v[j] = (j < c) ? __ldg(xr + j) : -INFINITY;
-        mx = fmaxf(mx, v[j]);
+        for (int j = 0; j < CMAX; j += 4) {
+          if (j < c) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(xr + j));
+            v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+          } else {
+            v[j] = v[j + 1] = v[j + 2] = v[j + 3] = -INFINITY;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CMAX; ++j) v[j] = (j < c) ? __ldg(xr + j) : -INFINITY;
       }
+#pragma unroll
+      for (int j = 0; j < CMAX; ++j) mx = fmaxf(mx, v[j]);
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < CMAX; ++j) {
@@ -34,20 +46,34 @@ nll_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int c, const int6
         s += v[j];
       }
       const int lab = (int)labels[i];
-      const float xl = __ldg(xr + lab);
+      const float xl = __ldg(xr + lab);  // L1 hit
       li = (logf(s) + mx - xl) * scale;
       if (dx) {
         const float rs = scale / s;
         float* d = dx + i * lddx;
+        if (vec_d) {
 #pragma unroll
-        for (int j = 0; j < CMAX; ++j)
-          if (j < c) d[j] = v[j] * rs - (j == lab ? scale : 0.f);
+          for (int j = 0; j < CMAX; j += 4)
+            if (j < c)
+              *reinterpret_cast<float4*>(d + j) = make_float4(v[j] * rs - (j == lab ? scale : 0.f), v[j + 1] * rs - (j + 1 == lab ? scale : 0.f),
+                                                              v[j + 2] * rs - (j + 2 == lab ? scale : 0.f), v[j + 3] * rs - (j + 3 == lab ? scale : 0.f));
+        } else {
+#pragma unroll
+          for (int j = 0; j < CMAX; ++j)
+            if (j < c) d[j] = v[j] * rs - (j == lab ? scale : 0.f);
+        }
       }
     } else if (dx) {
       float* d = dx + i * lddx;
+      if (vec_d) {
 #pragma unroll
-      for (int j = 0; j < CMAX; ++j)
-        if (j < c) d[j] = 0.f;
+        for (int j = 0; j < CMAX; j += 4)
+          if (j < c) *reinterpret_cast<float4*>(d + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CMAX; ++j)
+          if (j < c) d[j] = 0.f;
+      }
     }
   }
   // block reduction of the loss, one atomic per block
@@ -76,10 +102,12 @@ extern "C" int acm_nll_log_softmax(const float* logits, int64_t ld, int64_t n_ro
   const int64_t blocks = (n_rows + 255) / 256;
   ACM_CHECK_ARG(blocks < (1ll << 31), "nll_log_softmax: too many rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (n_classes <= 8) nll_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(logits, ld, n_rows, n_classes, labels, mask, scale, loss_sum, dlogits, ld_d);
-  else if (n_classes <= 16) nll_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(logits, ld, n_rows, n_classes, labels, mask, scale, loss_sum, dlogits, ld_d);
-  else if (n_classes <= 32) nll_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(logits, ld, n_rows, n_classes, labels, mask, scale, loss_sum, dlogits, ld_d);
-  else nll_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(logits, ld, n_rows, n_classes, labels, mask, scale, loss_sum, dlogits, ld_d);
+  const int vec = (n_classes % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  const int vec_d = dlogits && (n_classes % 4 == 0) && (ld_d % 4 == 0) && ((reinterpret_cast<uintptr_t>(dlogits) & 15) == 0);
+  if (n_classes <= 8) nll_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(logits, ld, n_rows, n_classes, labels, mask, scale, loss_sum, dlogits, ld_d, vec, vec_d);
+  else if (n_classes <= 16) nll_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(logits, ld, n_rows, n_classes, labels, mask, scale, loss_sum, dlogits, ld_d, vec, vec_d);
+  else if (n_classes <= 32) nll_kernel<32><<<(unsigned)blocks, 256, 0, st>>>(logits, ld, n_rows, n_classes, labels, mask, scale, loss_sum, dlogits, ld_d, vec, vec_d);
+  else nll_kernel<64><<<(unsigned)blocks, 256, 0, st>>>(logits, ld, n_rows, n_classes, labels, mask, scale, loss_sum, dlogits, ld_d, vec, vec_d);
   ACM_LAUNCH_CHECK("nll_log_softmax");
   return 0;
 }

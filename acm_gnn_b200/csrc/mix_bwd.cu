@@ -29,6 +29,7 @@ struct BwdParams {
   void* dh_all;
   void* dos_pre;
   float* dpack;
+  PeerTables peers;   // optional push of the [dS_L|dS_H] rows into every rank's table
 };
 
 constexpr int kBwdWarps = 8;
@@ -222,12 +223,18 @@ __global__ void __launch_bounds__(kBwdWarps * 32) mix_bwd_kernel(const BwdParams
     }
     if (valid) {
       float out[8];
-      T* tl = reinterpret_cast<T*>(p.t_lh) + row * TW + f0;
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) out[t] = (p.variant || o[k][t] > 0.f) ? dO[k][t] : 0.f;
-        Slice8<T>::store(tl + k * FP, out);
+        if (p.peers.n > 0) {
+          // fused all-gather of the backward operand table (see PeerTables)
+          const int64_t off = (p.peers.row_off + row) * TW + f0 + k * FP;
+#pragma unroll 1
+          for (int r = 0; r < p.peers.n; ++r) Slice8<T>::store(reinterpret_cast<T*>(p.peers.tables[r]) + off, out);
+        } else {
+          Slice8<T>::store(reinterpret_cast<T*>(p.t_lh) + row * TW + f0 + k * FP, out);
+        }
       }
 #pragma unroll
       for (int t = 0; t < 8; ++t) out[t] = (o[2][t] > 0.f) ? dO[2][t] : 0.f;
@@ -303,17 +310,23 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
                            const float* g, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
                            const float* att, const float* sig, const float* pack,
                            int k_channels, int ln_live, int variant, float out_scale,
-                           void* t_lh, void* dh_all, void* dos_pre, float* dpack, void* stream) {
+                           void* t_lh, void* dh_all, void* dos_pre, float* dpack,
+                           void* const* peer_tables, int n_peers, int64_t peer_row_off, void* stream) {
   using namespace acm;
+  ACM_CHECK_ARG(n_peers >= 0 && n_peers <= kMaxPeers, "mix_bwd: 0 <= n_peers <= %d", kMaxPeers);
+  ACM_CHECK_ARG(n_peers == 0 || peer_tables, "mix_bwd: peer push needs peer_tables");
   ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "mix_bwd: bad dtype %d", dtype);
   ACM_CHECK_ARG(k_channels == 3 || k_channels == 4, "mix_bwd: k_channels must be 3 or 4");
   ACM_CHECK_ARG(f >= 1 && f <= fp, "mix_bwd: need 1 <= f <= fp");
   ACM_CHECK_ARG(k_channels == 3 || (o_s && dos_pre), "mix_bwd: 4 channels need o_s and dos_pre");
-  ACM_CHECK_ARG(g && o_lh && h_i && att && sig && pack && t_lh && dh_all && dpack, "mix_bwd: null pointer");
+  ACM_CHECK_ARG(g && o_lh && h_i && att && sig && pack && (t_lh || n_peers > 0) && dh_all && dpack, "mix_bwd: null pointer");
   BwdParams p;
   p.n_rows = n_rows; p.g = g; p.ldg = ldg; p.o_lh = o_lh; p.h_i = h_i; p.o_s = o_s; p.att = att; p.sig = sig;
   p.pack = pack; p.k = k_channels; p.ln = ln_live; p.variant = variant; p.f = f; p.out_scale = out_scale;
   p.t_lh = t_lh; p.dh_all = dh_all; p.dos_pre = dos_pre; p.dpack = dpack;
+  p.peers = PeerTables{};
+  p.peers.n = n_peers; p.peers.row_off = peer_row_off;
+  for (int r = 0; r < n_peers; ++r) p.peers.tables[r] = peer_tables[r];
   p.vec_g = (f % 4 == 0) && (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int mode = (k_channels == 4 || ln_live) ? 1 : 0;

@@ -12,6 +12,9 @@ Works with the gloo backend on CPU tensors too, which is how the host logic is t
 """
 from __future__ import annotations
 
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -27,6 +30,8 @@ class RowPartition:
         self.r1 = min(self.n_global, self.r0 + self.rows_per_rank)
         self.n_local = self.r1 - self.r0
         self.bytes_gathered = 0
+        self._symm = {}
+        self._push_ok = None
 
     def bounds(self, rank):
         r0 = min(self.n_global, rank * self.rows_per_rank)
@@ -47,6 +52,42 @@ class RowPartition:
         dist.all_gather_into_tensor(out, local.contiguous(), group=self.group)
         self.bytes_gathered += out.numel() * out.element_size()
         return out
+
+    # -- fused exchange: tables in symmetric (peer-mapped) memory ---------------------------------
+    def push_enabled(self) -> bool:
+        """Kernels store operand-table rows straight into every rank's table over NVLink peer
+        mappings (csrc PeerTables) instead of a separate NCCL all-gather.  Needs CUDA symmetric
+        memory across the ranks of one box (<= 8); ACMB200_PUSH=0 forces the NCCL path."""
+        if self._push_ok is None:
+            ok = os.environ.get("ACMB200_PUSH", "1") != "0" and self.world <= 8 and torch.cuda.is_available()
+            if ok:
+                try:  # probe once: a tiny symmetric allocation + rendezvous (collective over the group)
+                    import torch.distributed._symmetric_memory as symm
+                    t = symm.empty((1024,), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+                    hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+                    ok = len(hdl.buffer_ptrs) == self.world
+                    hdl.barrier(channel=0)
+                    self._probe = (t, hdl)
+                except Exception as e:  # NCCL all-gather remains the exchange
+                    import warnings
+                    warnings.warn(f"acm_gnn_b200: symmetric memory unavailable ({e!r}); using NCCL all-gather")
+                    ok = False
+            self._push_ok = ok
+        return self._push_ok
+
+    def symm_table(self, key, width, dtype, device):
+        """Persistent [world*rows_per_rank, width] table in symmetric memory, one per (layer,
+        direction).  Returns (tensor, handle, ctypes array of the ``world`` peer base pointers)."""
+        k = (key, width, dtype)
+        hit = self._symm.get(k)
+        if hit is not None:
+            return hit
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty((self.world * self.rows_per_rank, width), dtype=dtype, device=device)
+        hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+        ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
+        self._symm[k] = (t, hdl, ptrs)
+        return self._symm[k]
 
     def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)

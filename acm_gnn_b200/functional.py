@@ -11,6 +11,7 @@ Math (validated against the reference, SURVEY.md section 8a / DESIGN.md):
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from dataclasses import dataclass
 from typing import Optional
@@ -44,6 +45,7 @@ class LayerConfig:
     gemm: str = "auto"         # "simt" | "tcgen05" | "auto"
     reorder: str = "env"       # aggregate-first order A(XW) = (AX)W: "auto" | "off" | "env" (ACMB200_REORDER)
     dist: Optional[object] = None   # acm_gnn_b200.dist.RowPartition or None
+    layer_key: int = 0              # identifies the layer's persistent symmetric-memory tables
 
     def storage(self):
         return (torch.bfloat16, _lib.ACM_BF16) if self.dtype == "bf16" else (torch.float32, _lib.ACM_F32)
@@ -205,10 +207,10 @@ class AcmLayerFunction(torch.autograd.Function):
 
         impl = cfg.gemm_impl(fin)
         agg_first = use_aggregate_first(cfg, fin, fp, bool(ctx.needs_input_grad[2]))
-        h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
         h_i = torch.empty(n, fp, dtype=tdt, device=dev)
-        z = d = wcat_t = None
+        z = d = wcat_t = h_lh = None
         if agg_first:
+            h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
             # ---- aggregate-first: Z = A X, D = X - Z, then [S_L|S_H|HI] = [Z W_L | D W_H | X W_I] ----
             ldx = padded_width(fin)
             if staged is not None:
@@ -254,9 +256,21 @@ class AcmLayerFunction(torch.autograd.Function):
             if impl == _lib.GEMM_TCGEN05:
                 wcat_t = torch.zeros(3 * fp, ldx, dtype=tdt, device=dev)
                 wcat_t[:, :fin] = wcat.t()
-            _lib.call("acm_gemm_xw_fwd", impl, cdt, xs.data_ptr(), ldx, wcat.data_ptr(), _lib.ptr(wcat_t),
-                      h_lh.data_ptr(), h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
-            table = h_lh if cfg.dist is None else cfg.dist.all_gather_rows(h_lh)
+            push = cfg.dist is not None and impl == _lib.GEMM_TCGEN05 and cfg.dist.push_enabled()
+            if push:
+                # fused GEMM + all-gather: the epilogue stores every finished [HL|HH] row into all
+                # ranks' tables through NVLink peer mappings; barriers order reuse of the table
+                table, hdl, ptrs = cfg.dist.symm_table((cfg.layer_key, "fwd"), 2 * fp, tdt, dev)
+                hdl.barrier(channel=0)     # every rank is done reading the previous contents
+                _lib.call("acm_gemm_xw_fwd_push", xs.data_ptr(), ldx, wcat_t.data_ptr(), ctypes.addressof(ptrs),
+                          cfg.dist.world, op.row0, h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
+                hdl.barrier(channel=1)     # every rank's rows have landed everywhere
+                h_lh = table[op.row0:op.row0 + n]
+            else:
+                h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
+                _lib.call("acm_gemm_xw_fwd", impl, cdt, xs.data_ptr(), ldx, wcat.data_ptr(), _lib.ptr(wcat_t),
+                          h_lh.data_ptr(), h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
+                table = h_lh if cfg.dist is None else cfg.dist.all_gather_rows(h_lh)
             csr = (op.low.rowptr.data_ptr(), op.low.col.data_ptr(), op.low.val.data_ptr())
             row0 = op.row0
             lr = _long_pass(op.low, False, table, fp, 2, cdt, st)
@@ -309,13 +323,26 @@ class AcmLayerFunction(torch.autograd.Function):
         st = _stream()
         g = g.contiguous().to(torch.float32)
 
-        t_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
         dh_all = torch.empty(n, 3 * fp, dtype=tdt, device=dev)
         dos_pre = torch.empty(n, fp, dtype=tdt, device=dev) if K == 4 else None
         dpack = torch.zeros(12 * fp + 16, dtype=torch.float32, device=dev)
-        _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
-                  att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
-                  float(cfg.out_scale), t_lh.data_ptr(), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(), st, tag=fp)
+        push = (cfg.dist is not None and not ctx.agg_first and cfg.dist.push_enabled())
+        if push:
+            # fused mix_bwd + all-gather of the backward operand table (peer stores over NVLink)
+            t_table, hdl, ptrs = cfg.dist.symm_table((cfg.layer_key, "bwd"), 2 * fp, tdt, dev)
+            hdl.barrier(channel=0)
+            _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
+                      att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
+                      float(cfg.out_scale), 0, dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
+                      ctypes.addressof(ptrs), cfg.dist.world, op.row0, st, tag=fp)
+            hdl.barrier(channel=1)
+            t_lh = None
+        else:
+            t_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
+            _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
+                      att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
+                      float(cfg.out_scale), t_lh.data_ptr(), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
+                      0, 0, 0, st, tag=fp)
 
         dwcat = torch.zeros(fin, 3 * fp, dtype=torch.float32, device=dev)
         dx = None
@@ -327,7 +354,8 @@ class AcmLayerFunction(torch.autograd.Function):
                 _lib.call("acm_gemm_atb", impl, cdt, a_op.data_ptr(), ldx, b_ptr, ldb,
                           dwcat[:, k * fp:].data_ptr(), 3 * fp, n, fin, fp, st, tag=fp)
         else:
-            t_table = t_lh if cfg.dist is None else cfg.dist.all_gather_rows(t_lh)
+            if not push:
+                t_table = t_lh if cfg.dist is None else cfg.dist.all_gather_rows(t_lh)
             lr = _long_pass(op.low, True, t_table, fp, 2, cdt, st)
             _lib.call("acm_spmm_t_bwd", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
                       op.low.val_t.data_ptr(), t_table.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(),

@@ -100,7 +100,7 @@ class GraphConvolution(nn.Module):
             raise RuntimeError("structure_info=1 is only valid with model_type acmgcnp/acmgcnpp")
         cfg = LayerConfig(variant=bool(self.variant), k_channels=4 if use_struct else 3, ln_live=ln_live,
                           out_scale=1.0 if use_struct else 3.0, dtype=self.acm_dtype, gemm=self.acm_gemm,
-                          dist=self.acm_dist)
+                          dist=self.acm_dist, layer_key=id(self))
         ln_flat = ()
         if ln_live:
             lns = [self.layer_norm_low, self.layer_norm_high, self.layer_norm_mlp] + (

@@ -89,6 +89,15 @@ int acm_cast_pad(const float* src, int64_t rows, int64_t cols, int64_t ld_src,
 int acm_gemm_xw_fwd(int impl, int dtype, const void* x, int64_t ldx, const void* wcat, const void* wcat_t,
                     void* h_lh, void* h_i, int64_t n, int64_t fin, int64_t fp, int relu_lh, void* stream);
 
+/* Multi-GPU (1-D row partition): the same forward GEMM with the all-gather FUSED into its
+ * epilogue.  peer_tables is a HOST array of n_peers (<= 8) device pointers, the base of every
+ * rank's [N_pad, 2*fp] gather table mapped into this process (symmetric memory over NVLink);
+ * each finished [HL|HH] row is stored into all of them at row index row_off + local row, so the
+ * exchange overlaps the GEMM and no separate collective runs (tcgen05 / bf16 path only).
+ * acm_mix_bwd takes the same (peer_tables, n_peers, peer_row_off) triple for the backward table. */
+int acm_gemm_xw_fwd_push(const void* x, int64_t ldx, const void* wcat_t, void* const* peer_tables, int n_peers,
+                         int64_t row_off, void* h_i, int64_t n, int64_t fin, int64_t fp, int relu_lh, void* stream);
+
 /* autograd of the three torch.mm: dWcat[fin, 3*fp] (fp32, zeroed by caller; accumulated
  * atomically over split-K slices) = X^T . dH,  dH [n, 3*fp] = [dHL | dHH | dHI]. */
 int acm_gemm_bwd_dw(int impl, int dtype, const void* x, int64_t ldx, const void* dh,
@@ -153,7 +162,8 @@ int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
                 const float* g, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
                 const float* att, const float* sig, const float* pack,
                 int k_channels, int ln_live, int variant, float out_scale,
-                void* t_lh, void* dh_all, void* dos_pre, float* dpack, void* stream);
+                void* t_lh, void* dh_all, void* dos_pre, float* dpack,
+                void* const* peer_tables, int n_peers, int64_t peer_row_off, void* stream);
 
 /* Transposed aggregation (autograd of torch.spmm(adj_low,.) / torch.spmm(adj_high,.)):
  *   dHL = A_low^T dS_L ; dHH = dS_H - A_low^T dS_H     -> dh_all[:, 0:2fp]
