@@ -371,16 +371,27 @@ class AcmLayerFunction(torch.autograd.Function):
         d_struc = d_a_struc = None
         if K == 4:
             nr = ctx.struc_rows
-            if cfg.dist is not None:
-                raise NotImplementedError("structure channel under a row partition")
-            d_struc = torch.empty(nr, f, dtype=torch.float32, device=dev)
-            _lib.call("acm_spmm_plain", cdt, _lib.ACM_F32, fp, nr, op.raw.rowptr_t.data_ptr(), op.raw.col_t.data_ptr(),
-                      op.raw.val_t.data_ptr(), dos_pre.data_ptr(), d_struc.data_ptr(), f, f, 0, st)
-            d_a_struc = dpack[3 * fp:3 * fp + f].reshape(f, 1).clone()
+            if cfg.dist is None:
+                d_struc = torch.empty(nr, f, dtype=torch.float32, device=dev)
+                _lib.call("acm_spmm_plain", cdt, _lib.ACM_F32, fp, nr, op.raw.rowptr_t.data_ptr(), op.raw.col_t.data_ptr(),
+                          op.raw.val_t.data_ptr(), dos_pre.data_ptr(), d_struc.data_ptr(), f, f, 0, st)
+            else:
+                # row partition: gather every rank's rows of d O_S, aggregate the own rows of
+                # A_raw^T, then assemble the gradient of the REPLICATED struc_low parameter
+                dos_all = cfg.dist.all_gather_rows(dos_pre)
+                d_loc = torch.empty(n, f, dtype=torch.float32, device=dev)
+                _lib.call("acm_spmm_plain", cdt, _lib.ACM_F32, fp, n, op.raw.rowptr_t.data_ptr(), op.raw.col_t.data_ptr(),
+                          op.raw.val_t.data_ptr(), dos_all.data_ptr(), d_loc.data_ptr(), f, f, 0, st)
+                d_struc = torch.zeros(nr, f, dtype=torch.float32, device=dev)
+                d_struc[op.row0:op.row0 + n] = d_loc
+                cfg.dist.all_reduce_(d_struc)
+                del dos_all, d_loc
 
         if cfg.dist is not None:
             cfg.dist.all_reduce_(dwcat)
             cfg.dist.all_reduce_(dpack)
+        if K == 4:
+            d_a_struc = dpack[3 * fp:3 * fp + f].reshape(f, 1).clone()
 
         dw = [dwcat[:, k * fp:k * fp + f].contiguous() for k in range(3)]
         da = [dpack[k * fp:k * fp + f].reshape(f, 1).clone() for k in range(3)]

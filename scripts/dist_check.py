@@ -23,8 +23,10 @@ def main():
     from acm_gnn_b200.functional import nll_log_softmax
     L.device = dev
     ok_all = True
-    for mode, variant, n, staged in (("fp32", False, 5003, False), ("bf16", False, 5003, False), ("fp32", True, 4096, False),
-                                     ("fp32", False, 5003, True), ("bf16", False, 4100, True)):
+    for mode, variant, n, staged, struct in (("fp32", False, 5003, False, 0), ("bf16", False, 5003, False, 0),
+                                             ("fp32", True, 4096, False, 0), ("fp32", False, 5003, True, 0),
+                                             ("bf16", False, 4100, True, 0), ("bf16", True, 4100, False, 0),
+                                             ("fp32", False, 3001, False, 1), ("bf16", True, 3001, False, 1)):
         os.environ["ACMB200_DTYPE"] = mode
         fin, hid, ncls = 48, 64, 7
         g = torch.Generator(device=dev); g.manual_seed(5)
@@ -38,11 +40,12 @@ def main():
         labels = torch.randint(0, ncls, (n,), generator=g, device=dev)
         mask = (torch.rand(n, generator=g, device=dev) < 0.6).to(torch.uint8)
         ntr = int(mask.sum().item())
-        op = A.AcmOperator.from_edges(row, col, n)
+        op = A.AcmOperator.from_edges(row, col, n, with_raw=bool(struct))
+        mtype = "acmgcnp" if struct else "acmgcn"
 
         def build():
             torch.manual_seed(42)
-            return A.GCN(fin, hid, ncls, 2, n, 0.0, "acmgcn", 0, variant=variant).to(dev)
+            return A.GCN(fin, hid, ncls, 2, n, 0.0, mtype, struct, variant=variant).to(dev)
 
         # single-GPU reference (every rank computes it redundantly)
         m1 = build()
@@ -70,7 +73,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         ok_all = ok_all and bool(t.item())
         if rank == 0:
-            print(f"dist_check world={world} mode={mode} variant={variant} staged={staged} n={n}: out rel.err {e_out:.2e}, worst grad rel.fro {worst:.2e} -> {'OK' if t.item() else 'FAIL'}", flush=True)
+            print(f"dist_check world={world} mode={mode} variant={variant} staged={staged} struct={struct} push={part.push_enabled()} n={n}: out rel.err {e_out:.2e}, worst grad rel.fro {worst:.2e} -> {'OK' if t.item() else 'FAIL'}", flush=True)
     if rank == 0:
         print("DIST_CHECK", "PASS" if ok_all else "FAIL", flush=True)
     dist.destroy_process_group()
