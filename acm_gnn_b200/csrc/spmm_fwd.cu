@@ -38,46 +38,17 @@ constexpr int kFwdWarps = 8;
 constexpr int kUnroll = 4;
 
 template <typename T, int FP, int MODE>
-__global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdParams p) {
+__device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t rb, const float* s_a,
+                                              const float* s_avec, const float* s_ga, const float* s_sc) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
   constexpr int KMAX = MODE ? 4 : 3;
   constexpr int TW = 2 * FP;  // table row width (elements)
-
-  extern __shared__ float smem[];
-  float* s_a = smem;                 // [KMAX][FP]   a_k
-  float* s_avec = s_a + KMAX * FP;   // [16]
-  float* s_ga = s_avec + 16;         // MODE 1: [4][FP] gamma*a
-  float* s_sc = s_ga + (MODE ? 4 * FP : 0);  // MODE 1: [8] sum(beta*a) per channel
-
   const int K = MODE ? p.k : 3;
-  for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) s_a[i] = p.pack[i];
-  if (threadIdx.x < 16) s_avec[threadIdx.x] = p.pack[pack_off_avec(FP) + threadIdx.x];
-  if (MODE) {
-    if (p.ln) {
-      for (int i = threadIdx.x; i < 4 * FP; i += blockDim.x)
-        s_ga[i] = p.pack[pack_off_gamma(FP, 0) + i] * p.pack[i];
-      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-      if (w < 4) {
-        float sb = 0.f;
-        for (int i = l; i < FP; i += 32) sb += p.pack[pack_off_beta(FP, w) + i] * p.pack[pack_off_a(FP, w) + i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        if (l == 0) s_sc[w] = sb;
-      }
-    }
-  }
-  __syncthreads();
-
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int sub = lane / LANES;
   const int gl = lane % LANES;
-  // one pass per block in gather mode (the hardware block scheduler balances the degrees);
-  // grid-stride in the pre-aggregated mode, where a block's rows are too little work to
-  // amortise the parameter-pack load above
-  const int64_t n_blocks = (p.n_rows + (int64_t)kFwdWarps * RPW - 1) / ((int64_t)kFwdWarps * RPW);
-  for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) {
   const int64_t row = (rb * kFwdWarps + warp) * RPW + sub;
   const bool valid = row < p.n_rows;
 
@@ -246,7 +217,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) a[k] *= rden;
 
-  if (!valid) continue;
+  if (!valid) return;
 
   float yv[8];
 #pragma unroll
@@ -277,7 +248,50 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
       if (p.sig) p.sig[row * K + k] = s[k];
     }
   }
-  }  // row-block loop
+}
+
+template <typename T, int FP, int MODE>
+__global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdParams p) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPW = 32 / LANES;
+  constexpr int KMAX = MODE ? 4 : 3;
+  constexpr int TW = 2 * FP;  // table row width (elements)
+
+  extern __shared__ float smem[];
+  float* s_a = smem;                 // [KMAX][FP]   a_k
+  float* s_avec = s_a + KMAX * FP;   // [16]
+  float* s_ga = s_avec + 16;         // MODE 1: [4][FP] gamma*a
+  float* s_sc = s_ga + (MODE ? 4 * FP : 0);  // MODE 1: [8] sum(beta*a) per channel
+
+  const int K = MODE ? p.k : 3;
+  for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) s_a[i] = p.pack[i];
+  if (threadIdx.x < 16) s_avec[threadIdx.x] = p.pack[pack_off_avec(FP) + threadIdx.x];
+  if (MODE) {
+    if (p.ln) {
+      for (int i = threadIdx.x; i < 4 * FP; i += blockDim.x)
+        s_ga[i] = p.pack[pack_off_gamma(FP, 0) + i] * p.pack[i];
+      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+      if (w < 4) {
+        float sb = 0.f;
+        for (int i = l; i < FP; i += 32) sb += p.pack[pack_off_beta(FP, w) + i] * p.pack[pack_off_a(FP, w) + i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        if (l == 0) s_sc[w] = sb;
+      }
+    }
+  }
+  __syncthreads();
+
+  constexpr int RPWk = 32 / (FP / 8);
+  if (p.pre_agg) {
+    // pre-aggregated (aggregate-first) mode: a block's rows are too little work to amortise the
+    // parameter-pack load above -> grid-stride over row blocks
+    const int64_t n_blocks = (p.n_rows + (int64_t)kFwdWarps * RPWk - 1) / ((int64_t)kFwdWarps * RPWk);
+    for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) fwd_row_block<T, FP, MODE>(p, rb, s_a, s_avec, s_ga, s_sc);
+  } else {
+    // gather mode: one row block per CTA; the hardware block scheduler balances the degrees
+    fwd_row_block<T, FP, MODE>(p, blockIdx.x, s_a, s_avec, s_ga, s_sc);
+  }
 }
 
 template <typename T, int FP, int MODE>
