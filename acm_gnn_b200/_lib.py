@@ -29,14 +29,15 @@ _PROTOS = {
     "acm_gemm_bwd_dw": [_i32, _i32, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp],
     "acm_gemm_bwd_dx": [_i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp],
     "acm_spmm_mix_fwd": [_i32, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                         _i32, _i32, _i32, _f32, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+                         _i32, _i32, _i32, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
     "acm_spmm_long_rows": [_i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
-    "acm_mix_bwd": [_i32, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+    "acm_mix_bwd": [_i32, _i32, _i32, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                     _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp],
     "acm_gemm_xw_fwd_push": [_vp, _i64, _vp, _vp, _i32, _i64, _vp, _i64, _i64, _i64, _i32, _vp],
     "acm_spmm_t_bwd": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
     "acm_nll_log_softmax": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _i64, _vp],
     "acm_set_l2_fetch_granularity": [_i32],
+    "acm_set_gather_mode": [_i32],
     "acm_gemm_ab": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "acm_gemm_atb": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp],
     "acm_spmm_agg_first": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
@@ -71,6 +72,9 @@ def load():
             fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, _c.c_int)
+        g = os.environ.get("ACMB200_GATHER")
+        if g is not None:
+            lib.acm_set_gather_mode(1 if g.lower() in ("1", "async", "cp.async") else 0)
         _lib = lib
     return _lib
 

@@ -23,7 +23,7 @@ struct BwdParams {
   const float* att;
   const float* sig;
   const float* pack;
-  int k, ln, variant, f, vec_g;
+  int k, ln, variant, f, vec_g, g_bf16;
   float out_scale;
   void* t_lh;
   void* dh_all;
@@ -119,7 +119,17 @@ __global__ void __launch_bounds__(kBwdWarps * 32) mix_bwd_kernel(const BwdParams
     }
     if (valid) {
       const float* gr = p.g + row * p.ldg + f0;
-      if (p.vec_g && f0 + 8 <= p.f) {
+      if (p.g_bf16) {
+        const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(p.g) + row * p.ldg + f0;
+        if (p.vec_g && f0 + 8 <= p.f) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(gb));
+          unpack_bf16x8(v, G);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            if (f0 + t < p.f) G[t] = __bfloat162float(gb[t]);
+        }
+      } else if (p.vec_g && f0 + 8 <= p.f) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(gr));
         const float4 b = __ldg(reinterpret_cast<const float4*>(gr) + 1);
         G[0] = a.x; G[1] = a.y; G[2] = a.z; G[3] = a.w;
@@ -307,7 +317,7 @@ static int launch_bwd(const BwdParams& p, cudaStream_t st) {
 }  // namespace acm
 
 extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
-                           const float* g, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
+                           const void* g, int g_dtype, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
                            const float* att, const float* sig, const float* pack,
                            int k_channels, int ln_live, int variant, float out_scale,
                            void* t_lh, void* dh_all, void* dos_pre, float* dpack,
@@ -321,13 +331,15 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
   ACM_CHECK_ARG(k_channels == 3 || (o_s && dos_pre), "mix_bwd: 4 channels need o_s and dos_pre");
   ACM_CHECK_ARG(g && o_lh && h_i && att && sig && pack && (t_lh || n_peers > 0) && dh_all && dpack, "mix_bwd: null pointer");
   BwdParams p;
-  p.n_rows = n_rows; p.g = g; p.ldg = ldg; p.o_lh = o_lh; p.h_i = h_i; p.o_s = o_s; p.att = att; p.sig = sig;
+  ACM_CHECK_ARG(g_dtype == ACM_F32 || g_dtype == ACM_BF16, "mix_bwd: bad g dtype %d", g_dtype);
+  p.n_rows = n_rows; p.g = reinterpret_cast<const float*>(g); p.ldg = ldg; p.g_bf16 = (g_dtype == ACM_BF16); p.o_lh = o_lh; p.h_i = h_i; p.o_s = o_s; p.att = att; p.sig = sig;
   p.pack = pack; p.k = k_channels; p.ln = ln_live; p.variant = variant; p.f = f; p.out_scale = out_scale;
   p.t_lh = t_lh; p.dh_all = dh_all; p.dos_pre = dos_pre; p.dpack = dpack;
   p.peers = PeerTables{};
   p.peers.n = n_peers; p.peers.row_off = peer_row_off;
   for (int r = 0; r < n_peers; ++r) p.peers.tables[r] = peer_tables[r];
-  p.vec_g = (f % 4 == 0) && (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  p.vec_g = p.g_bf16 ? ((f % 8 == 0) && (ldg % 8 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0))
+                     : ((f % 4 == 0) && (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int mode = (k_channels == 4 || ln_live) ? 1 : 0;
   if (dtype == ACM_BF16) {

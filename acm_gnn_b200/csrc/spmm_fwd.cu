@@ -24,7 +24,7 @@ struct FwdParams {
   const void* h_i;
   const void* o_s;
   const float* pack;
-  int k, ln, variant, f, vec_y, pre_agg;
+  int k, ln, variant, f, vec_y, pre_agg, y_bf16;
   float out_scale;
   float* y;
   int64_t ldy;
@@ -37,9 +37,30 @@ struct FwdParams {
 constexpr int kFwdWarps = 8;
 constexpr int kUnroll = 4;
 
-template <typename T, int FP, int MODE>
+// ---- asynchronous gather (cp.async ring in shared memory) ---------------------------------------
+// Each lane copies its own two 8-feature slices of a neighbour row straight from global to shared
+// memory (LDGSTS, no register staging) kAsyncBytes/row-slot deep, so the number of neighbour rows
+// in flight per lane is fixed by the ring depth instead of by ptxas' register-pressure driven load
+// scheduling (which, capped at 64 registers, interleaved the LDGs with the FMAs and left ~2 rows
+// in flight).  A lane only ever reads back the bytes it copied itself: no warp synchronisation.
+template <typename T> struct AsyncCfg { static constexpr int kStages = sizeof(T) == 2 ? 8 : 4; };
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <typename T> __device__ __forceinline__ void cp_async_slice(uint32_t dst, const T* src) {
+  cp_async16(dst, src);
+  if (sizeof(T) == 4) cp_async16(dst + 16, reinterpret_cast<const char*>(src) + 16);
+}
+
+template <typename T, int FP, int MODE, bool ASYNC>
 __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t rb, const float* s_a,
-                                              const float* s_avec, const float* s_ga, const float* s_sc) {
+                                              const float* s_avec, const float* s_ga, const float* s_sc,
+                                              uint8_t* s_ring) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
   constexpr int KMAX = MODE ? 4 : 3;
@@ -72,6 +93,47 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
     for (int t = 0; t < 8; ++t) {
       accL[t] = a[t];
       accH[t] = a[FP + t];
+    }
+    e = e1;
+  }
+
+  if (ASYNC && e < e1) {
+    constexpr int ST = AsyncCfg<T>::kStages;
+    constexpr int SB = 8 * (int)sizeof(T);           // bytes of one 8-feature slice
+    constexpr int STAGE_BYTES = 64 * SB;             // per warp: 32 L slices then 32 H slices
+    uint8_t* ring = s_ring + warp * (ST * STAGE_BYTES);
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring) + lane * SB;
+    const int n_e = (int)(e1 - e);
+#pragma unroll
+    for (int st = 0; st < ST; ++st) {
+      if (st < n_e) {
+        const T* r = tab + (int64_t)__ldg(col + e + st) * TW;
+        cp_async_slice<T>(ring_u32 + st * STAGE_BYTES, r);
+        cp_async_slice<T>(ring_u32 + st * STAGE_BYTES + 32 * SB, r + FP);
+      }
+      cp_async_commit();
+    }
+    for (int i = 0; i < n_e; ++i) {
+      cp_async_wait<ST - 1>();                        // the oldest group (edge i) has landed
+      const float w = val ? __ldg(val + e + i) : 1.f;
+      const int slot = i & (ST - 1);
+      Slice8<T> vl, vh;
+      vl.load_plain(reinterpret_cast<const T*>(ring + slot * STAGE_BYTES + lane * SB));
+      vh.load_plain(reinterpret_cast<const T*>(ring + slot * STAGE_BYTES + 32 * SB + lane * SB));
+      float fl[8], fh[8];
+      vl.to_float(fl);
+      vh.to_float(fh);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        accL[t] = fmaf(w, fl[t], accL[t]);
+        accH[t] = fmaf(w, fh[t], accH[t]);
+      }
+      if (i + ST < n_e) {
+        const T* r = tab + (int64_t)__ldg(col + e + i + ST) * TW;
+        cp_async_slice<T>(ring_u32 + slot * STAGE_BYTES, r);
+        cp_async_slice<T>(ring_u32 + slot * STAGE_BYTES + 32 * SB, r + FP);
+      }
+      cp_async_commit();
     }
     e = e1;
   }
@@ -228,8 +290,20 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
     yv[t] = p.out_scale * acc;
   }
   const int f0 = gl * 8;
+  if (p.y_bf16) {
+    // bf16 inter-layer activations (the next layer's bf16 cast folded in here)
+    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + f0;
+    if (p.vec_y && f0 + 8 <= p.f) {
+      *reinterpret_cast<uint4*>(yb) = pack_bf16x8(yv);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (f0 + t < p.f) yb[t] = __float2bfloat16_rn(yv[t]);
+    }
+  }
   float* yr = p.y + row * p.ldy + f0;
-  if (p.vec_y && f0 + 8 <= p.f) {
+  if (p.y_bf16) {
+  } else if (p.vec_y && f0 + 8 <= p.f) {
     *reinterpret_cast<float4*>(yr) = make_float4(yv[0], yv[1], yv[2], yv[3]);
     *reinterpret_cast<float4*>(yr + 4) = make_float4(yv[4], yv[5], yv[6], yv[7]);
   } else {
@@ -250,7 +324,7 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
   }
 }
 
-template <typename T, int FP, int MODE>
+template <typename T, int FP, int MODE, bool ASYNC>
 __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdParams p) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
@@ -287,12 +361,18 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
     // pre-aggregated (aggregate-first) mode: a block's rows are too little work to amortise the
     // parameter-pack load above -> grid-stride over row blocks
     const int64_t n_blocks = (p.n_rows + (int64_t)kFwdWarps * RPWk - 1) / ((int64_t)kFwdWarps * RPWk);
-    for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x) fwd_row_block<T, FP, MODE>(p, rb, s_a, s_avec, s_ga, s_sc);
+    for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x)
+      fwd_row_block<T, FP, MODE, false>(p, rb, s_a, s_avec, s_ga, s_sc, nullptr);
   } else {
     // gather mode: one row block per CTA; the hardware block scheduler balances the degrees
-    fwd_row_block<T, FP, MODE>(p, blockIdx.x, s_a, s_avec, s_ga, s_sc);
+    // the cp.async ring follows the parameter pack in dynamic shared memory (16-byte aligned)
+    constexpr int kPackFloats = (MODE ? 4 : 3) * FP + 16 + (MODE ? 4 * FP + 8 : 0);
+    uint8_t* s_ring = reinterpret_cast<uint8_t*>(smem + ((kPackFloats + 3) & ~3));
+    fwd_row_block<T, FP, MODE, ASYNC>(p, blockIdx.x, s_a, s_avec, s_ga, s_sc, s_ring);
   }
 }
+
+static int g_gather_mode = 1;  // 0: LDG register staging, 1: cp.async shared-memory ring
 
 template <typename T, int FP, int MODE>
 static int launch_fwd(const FwdParams& p, cudaStream_t st) {
@@ -302,8 +382,25 @@ static int launch_fwd(const FwdParams& p, cudaStream_t st) {
   if (blocks == 0) return 0;
   if (p.pre_agg && blocks > 148 * 16) blocks = 148 * 16;
   ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_mix_fwd: too many rows for one launch");
-  const size_t smem = sizeof(float) * ((MODE ? 4 : 3) * FP + 16 + (MODE ? 4 * FP + 8 : 0));
-  spmm_mix_fwd_kernel<T, FP, MODE><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
+  constexpr int kPackFloats = (MODE ? 4 : 3) * FP + 16 + (MODE ? 4 * FP + 8 : 0);
+  const bool async = g_gather_mode == 1 && !p.pre_agg;
+  size_t smem = sizeof(float) * ((kPackFloats + 3) & ~3);
+  if (async) {
+    smem += (size_t)kFwdWarps * AsyncCfg<T>::kStages * 64 * 8 * sizeof(T);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(spmm_mix_fwd_kernel<T, FP, MODE, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) {
+        set_error("spmm_mix_fwd: cannot raise dynamic shared memory to %zu: %s", smem, cudaGetErrorString(e));
+        return (int)e;
+      }
+      attr_set = true;
+    }
+    spmm_mix_fwd_kernel<T, FP, MODE, true><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
+  } else {
+    spmm_mix_fwd_kernel<T, FP, MODE, false><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
+  }
   ACM_LAUNCH_CHECK("spmm_mix_fwd");
   return 0;
 }
@@ -314,7 +411,7 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
                                 const int64_t* rowptr, const int32_t* col, const float* val, const float* rowscale,
                                 const void* table, const void* h_i, const void* o_s,
                                 const float* pack, int k_channels, int ln_live, int variant, float out_scale,
-                                float* y, int64_t ldy, void* o_save, float* att, float* sig,
+                                void* y, int y_dtype, int64_t ldy, void* o_save, float* att, float* sig,
                                 const int32_t* long_rows, int n_long, const float* long_acc, void* stream) {
   using namespace acm;
   ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_mix_fwd: bad dtype %d", dtype);
@@ -326,12 +423,15 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
   FwdParams p;
   p.n_rows = n_rows; p.row0 = row0; p.rowptr = rowptr; p.col = col; p.val = val; p.rowscale = rowscale;
   p.table = table; p.h_i = h_i; p.o_s = o_s; p.pack = pack; p.k = k_channels; p.ln = ln_live;
-  p.variant = variant; p.f = f; p.out_scale = out_scale; p.y = y; p.ldy = ldy; p.o_save = o_save;
+  ACM_CHECK_ARG(y_dtype == ACM_F32 || y_dtype == ACM_BF16, "spmm_mix_fwd: bad y dtype %d", y_dtype);
+  p.variant = variant; p.f = f; p.out_scale = out_scale; p.y = reinterpret_cast<float*>(y); p.ldy = ldy; p.o_save = o_save;
+  p.y_bf16 = (y_dtype == ACM_BF16);
   p.att = att; p.sig = sig;
   p.pre_agg = (rowptr == nullptr);
   p.lr.rows = n_long > 0 ? long_rows : nullptr; p.lr.acc = long_acc; p.lr.n_long = n_long;
   ACM_CHECK_ARG(n_long == 0 || (long_rows && long_acc), "spmm_mix_fwd: long rows need long_rows and long_acc");
-  p.vec_y = (f % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  p.vec_y = p.y_bf16 ? ((f % 8 == 0) && (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0))
+                     : ((f % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int mode = (k_channels == 4 || ln_live) ? 1 : 0;
   if (dtype == ACM_BF16) {
@@ -339,5 +439,14 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
   } else {
     ACM_DISPATCH_FP(fp, return mode ? launch_fwd<float, FP, 1>(p, st) : launch_fwd<float, FP, 0>(p, st));
   }
+  return 0;
+}
+
+extern "C" int acm_set_gather_mode(int mode) {
+  if (mode != 0 && mode != 1) {
+    acm::set_error("gather mode must be 0 (LDG) or 1 (cp.async ring)");
+    return ACM_ERR_BAD_ARG;
+  }
+  acm::g_gather_mode = mode;
   return 0;
 }

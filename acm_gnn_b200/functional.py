@@ -46,6 +46,7 @@ class LayerConfig:
     reorder: str = "env"       # aggregate-first order A(XW) = (AX)W: "auto" | "off" | "env" (ACMB200_REORDER)
     dist: Optional[object] = None   # acm_gnn_b200.dist.RowPartition or None
     layer_key: int = 0              # identifies the layer's persistent symmetric-memory tables
+    out_dtype: str = "fp32"         # dtype of Y: "fp32" (reference boundary) | "bf16" (inter-layer activations)
 
     def storage(self):
         return (torch.bfloat16, _lib.ACM_BF16) if self.dtype == "bf16" else (torch.float32, _lib.ACM_F32)
@@ -217,8 +218,11 @@ class AcmLayerFunction(torch.autograd.Function):
                 xs, x_all = staged.xs, staged.x_all
             else:
                 xc = x.detach().contiguous()
-                if cfg.dtype == "fp32" and ldx == fin:
+                if xc.dtype == tdt and ldx == fin:
                     xs = xc
+                elif xc.dtype != torch.float32:
+                    xs = torch.zeros(n, ldx, dtype=tdt, device=dev)
+                    xs[:, :fin] = xc
                 else:
                     xs = torch.empty(n, ldx, dtype=tdt, device=dev)
                     _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, xs.data_ptr(), cdt, ldx, st)
@@ -245,6 +249,17 @@ class AcmLayerFunction(torch.autograd.Function):
             # staging copy of the layer input in the storage dtype (row stride padded to 8)
             if staged is not None:
                 xs, ldx = staged.xs, staged.xs.shape[1]
+            elif x.dtype == torch.bfloat16:
+                # bf16 activations from the previous ACM layer: already in the storage dtype
+                if cfg.dtype != "bf16":
+                    raise ValueError("bf16 input needs ACMB200_DTYPE=bf16")
+                ldx = (fin + 7) // 8 * 8
+                xc = x.detach().contiguous()
+                if ldx == fin:
+                    xs = xc
+                else:
+                    xs = torch.zeros(n, ldx, dtype=tdt, device=dev)
+                    xs[:, :fin] = xc
             elif cfg.dtype == "bf16":
                 ldx = (fin + 7) // 8 * 8
                 xs = torch.empty(n, ldx, dtype=tdt, device=dev)
@@ -290,14 +305,18 @@ class AcmLayerFunction(torch.autograd.Function):
         # grad mode is off inside Function.forward: needs_input_grad is the reliable signal
         # (all False under torch.no_grad(), e.g. ACM-Geometric's evaluate_acmgcn)
         need_grad = any(ctx.needs_input_grad)
-        y = torch.empty(n, f, dtype=torch.float32, device=dev)
+        y_bf16 = (cfg.out_dtype == "bf16")
+        if y_bf16 and cfg.dtype != "bf16":
+            raise ValueError("bf16 activations need ACMB200_DTYPE=bf16")
+        y = torch.empty(n, f, dtype=torch.bfloat16 if y_bf16 else torch.float32, device=dev)
         att = torch.empty(n, K, dtype=torch.float32, device=dev)
         sig = torch.empty(n, K, dtype=torch.float32, device=dev) if need_grad else None
         o_save = torch.empty(n, 2 * fp, dtype=tdt, device=dev) if need_grad else None
         _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, row0, csr[0], csr[1], csr[2], 0,
                   table.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s), pack.data_ptr(),
                   K, int(cfg.ln_live), int(cfg.variant), float(cfg.out_scale),
-                  y.data_ptr(), f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig), lr[0], lr[1], lr[2], st, tag=fp)
+                  y.data_ptr(), _lib.ACM_BF16 if y_bf16 else _lib.ACM_F32, f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig),
+                  lr[0], lr[1], lr[2], st, tag=fp)
         del lr
 
         ctx.mark_non_differentiable(att)
@@ -305,6 +324,7 @@ class AcmLayerFunction(torch.autograd.Function):
             ctx.op, ctx.cfg = op, cfg
             ctx.dims = (n, fin, f, fp, K, ldx, impl)
             ctx.agg_first = agg_first
+            ctx.x_dtype = x.dtype
             ctx.x_needs_grad = bool(ctx.needs_input_grad[2])
             ctx.n_ln = len(ln_flat)
             ctx.struc_rows = 0 if struc_low is None else struc_low.shape[0]
@@ -321,7 +341,10 @@ class AcmLayerFunction(torch.autograd.Function):
         tdt, cdt = cfg.storage()
         dev = g.device
         st = _stream()
-        g = g.contiguous().to(torch.float32)
+        g = g.contiguous()
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.to(torch.float32)
+        gdt = _lib.ACM_BF16 if g.dtype == torch.bfloat16 else _lib.ACM_F32
 
         dh_all = torch.empty(n, 3 * fp, dtype=tdt, device=dev)
         dos_pre = torch.empty(n, fp, dtype=tdt, device=dev) if K == 4 else None
@@ -331,7 +354,7 @@ class AcmLayerFunction(torch.autograd.Function):
             # fused mix_bwd + all-gather of the backward operand table (peer stores over NVLink)
             t_table, hdl, ptrs = cfg.dist.symm_table((cfg.layer_key, "bwd"), 2 * fp, tdt, dev)
             hdl.barrier(channel=0)
-            _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
+            _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), gdt, f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
                       att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
                       float(cfg.out_scale), 0, dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
                       ctypes.addressof(ptrs), cfg.dist.world, op.row0, st, tag=fp)
@@ -339,7 +362,7 @@ class AcmLayerFunction(torch.autograd.Function):
             t_lh = None
         else:
             t_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
-            _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
+            _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), gdt, f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
                       att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
                       float(cfg.out_scale), t_lh.data_ptr(), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
                       0, 0, 0, st, tag=fp)
@@ -362,10 +385,18 @@ class AcmLayerFunction(torch.autograd.Function):
                       lr[0], lr[1], lr[2], st, tag=fp)
             del t_table, lr
             _lib.call("acm_gemm_bwd_dw", impl, cdt, xs.data_ptr(), ldx, dh_all.data_ptr(), dwcat.data_ptr(), n, fin, fp, st, tag=fp)
-            if ctx.x_needs_grad:
+            if ctx.x_needs_grad and ctx.x_dtype == torch.bfloat16 and fin % 8 == 0:
+                # bf16 activations: the gradient goes back in bf16 as well (dX = dH Wcat^T)
+                dx = torch.empty(n, fin, dtype=torch.bfloat16, device=dev)
+                wt = wcat_t if wcat_t is not None else wcat.t().contiguous()
+                _lib.call("acm_gemm_ab", impl, cdt, dh_all.data_ptr(), 3 * fp, wt.data_ptr(), wt.shape[1],
+                          wcat.data_ptr(), 3 * fp, dx.data_ptr(), fin, n, fin, 3 * fp, 0, st, tag=fp)
+            elif ctx.x_needs_grad:
                 dx = torch.empty(n, fin, dtype=torch.float32, device=dev)
                 _lib.call("acm_gemm_bwd_dx", impl, cdt, dh_all.data_ptr(), wcat.data_ptr(), _lib.ptr(wcat_t), ldx,
                           dx.data_ptr(), fin, n, fin, fp, st, tag=fp)
+                if ctx.x_dtype != torch.float32:
+                    dx = dx.to(ctx.x_dtype)
         del t_lh
 
         d_struc = d_a_struc = None

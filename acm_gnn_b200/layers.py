@@ -58,6 +58,7 @@ class GraphConvolution(nn.Module):
         self.acm_dtype = default_dtype()
         self.acm_gemm = os.environ.get("ACMB200_GEMM", "auto")
         self.acm_dist = None  # set by acm_gnn_b200.dist for row-partitioned multi-GPU runs
+        self.acm_out_dtype = "fp32"  # "bf16": emit bf16 activations for a following ACM layer (models.GCN opts in)
 
     def reset_parameters(self):
         # draw order of the reference (layers.py:70-92); bounds are 1/sqrt(size(1))
@@ -100,7 +101,8 @@ class GraphConvolution(nn.Module):
             raise RuntimeError("structure_info=1 is only valid with model_type acmgcnp/acmgcnpp")
         cfg = LayerConfig(variant=bool(self.variant), k_channels=4 if use_struct else 3, ln_live=ln_live,
                           out_scale=1.0 if use_struct else 3.0, dtype=self.acm_dtype, gemm=self.acm_gemm,
-                          dist=self.acm_dist, layer_key=id(self))
+                          dist=self.acm_dist, layer_key=id(self),
+                          out_dtype=self.acm_out_dtype if self.acm_dtype == "bf16" else "fp32")
         ln_flat = ()
         if ln_live:
             lns = [self.layer_norm_low, self.layer_norm_high, self.layer_norm_mlp] + (

@@ -43,6 +43,14 @@ class GCN(nn.Module):
         # (Y_f == 0 implies O_k,f == 0 for all k, whose relu masks already block that path).
         # Skipping it saves two [N, hidden] fp32 passes per step; results are bit-identical.
         self.skip_identity_relu = True
+        # bf16 inter-layer activations ("the next layer's bf16 cast"): in bf16
+        # storage mode layer 0 writes its output directly in bf16 -- the very values layer 1 would
+        # obtain by casting -- and receives its gradient in bf16; the reference glue in between
+        # (relu, dropout, + xX) is dtype-agnostic.  The model output (layer 1) stays fp32.
+        # ACMB200_BF16_ACT=0 keeps the fp32 boundary between the layers.
+        import os
+        if os.environ.get("ACMB200_BF16_ACT", "1") != "0":
+            self.gcns[0].acm_out_dtype = "bf16"
 
     def forward(self, x, adj_low, adj_high, adj_low_unnormalized):
         if isinstance(x, StagedInput):

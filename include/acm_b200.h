@@ -144,14 +144,20 @@ int acm_spmm_long_rows(int dtype, int fp, int halves, int64_t n_seg, const int32
  * Rows: this call computes rows [0,n_rows) whose global ids are row0+r; `table` is the
  * full (all-gathered) table indexed by global column ids.  val/rowscale may be NULL (=1).
  * o_save/sig may be NULL (inference).
+ * y is fp32 (the reference boundary) or, y_dtype = ACM_BF16, bf16 inter-layer activations
+ * (the next layer's input cast folded into this epilogue; acm_mix_bwd accepts g in bf16 likewise).
  * rowptr == col == NULL selects the pre-aggregated mode of the aggregate-first order: the
  * own rows of `table` already hold [S_L | S_H] and only the epilogue runs. */
 int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
                      const int64_t* rowptr, const int32_t* col, const float* val, const float* rowscale,
                      const void* table, const void* h_i, const void* o_s,
                      const float* pack, int k_channels, int ln_live, int variant, float out_scale,
-                     float* y, int64_t ldy, void* o_save, float* att, float* sig,
+                     void* y, int y_dtype, int64_t ldy, void* o_save, float* att, float* sig,
                      const int32_t* long_rows, int n_long, const float* long_acc, void* stream);
+
+/* Gather implementation of acm_spmm_mix_fwd: 1 (default) = cp.async ring in shared memory (each
+ * lane keeps 8 neighbour rows in flight without register staging), 0 = LDG register staging. */
+int acm_set_gather_mode(int mode);
 
 /* Row-local backward of the attention/mix/relu part (autograd of layers.py:94-152,
  * 185-204).  g = dL/dY [n_rows, f].  Writes t_lh [n_rows, 2*fp] = [dS_L | dS_H] (the table
@@ -159,7 +165,7 @@ int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
  * of the structure channel before its relu) and atomically accumulates the parameter
  * gradients into dpack (same layout as pack; zeroed by caller). */
 int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
-                const float* g, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
+                const void* g, int g_dtype, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
                 const float* att, const float* sig, const float* pack,
                 int k_channels, int ln_live, int variant, float out_scale,
                 void* t_lh, void* dh_all, void* dos_pre, float* dpack,

@@ -434,3 +434,50 @@ def test_degree_skew_long_rows_squirrel(order, mode, monkeypatch):
         _close_grad(xc.grad, xo.grad, mode, "dx")
     for k in ("weight_low", "weight_high", "weight_mlp", "att_vec_low", "att_vec"):
         _close_grad(getattr(layer, k).grad, p[k].grad, mode, "d" + k)
+
+
+@pytest.mark.parametrize("gather", ["0", "1"])
+def test_gather_modes_agree(gather):
+    """acm_set_gather_mode: the cp.async shared-memory ring and the LDG register-staged gather
+    produce the same sums (fp32 storage: identical accumulation order -> bitwise equal)."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    os.environ["ACMB200_DTYPE"] = "fp32"
+    os.environ["ACMB200_REORDER"] = "off"
+    try:
+        g = Golden("gcn_pt_acmgcn_v0")
+        model = _cuda_model(g, "fp32")
+        op = A.AcmOperator.from_edges(torch.from_numpy(g.row).cuda(), torch.from_numpy(g.col).cuda(), g.n)
+        x = g.x.cuda()
+        _lib.call("acm_set_gather_mode", int(gather))
+        out = model(x, op, None, None)
+        _lib.call("acm_set_gather_mode", 0)
+        ref = model(x, op, None, None)
+        assert torch.equal(out, ref)
+        _close(out, g.z["out"], "fp32", "out")
+    finally:
+        _lib.call("acm_set_gather_mode", 1)
+        os.environ.pop("ACMB200_REORDER", None)
+
+
+def test_bf16_interlayer_activations_equivalent(monkeypatch):
+    """models.GCN lets layer 0 emit bf16 activations (the values layer 1 would obtain by casting):
+    the forward output is bit-identical to the fp32-boundary run; gradients agree to bf16 noise."""
+    import acm_gnn_b200 as A
+    os.environ["ACMB200_DTYPE"] = "bf16"
+    g = Golden("gcn_pt_acmgcn_v0")
+    op = A.AcmOperator.from_edges(torch.from_numpy(g.row).cuda(), torch.from_numpy(g.col).cuda(), g.n)
+    x = g.x.cuda()
+    res = {}
+    for act in ("1", "0"):
+        monkeypatch.setenv("ACMB200_BF16_ACT", act)
+        model = _cuda_model(g, "bf16")
+        assert model.gcns[0].acm_out_dtype == ("bf16" if act == "1" else "fp32")
+        out = model(x, op, None, None)
+        assert out.dtype == torch.float32
+        out.square().sum().backward()
+        res[act] = (out.detach().clone(), model.gcns[0].weight_low.grad.detach().clone(),
+                    model.gcns[1].weight_low.grad.detach().clone())
+    assert torch.equal(res["1"][0], res["0"][0])
+    _close_grad(res["1"][1], res["0"][1], "bf16", "dW0")
+    _close_grad(res["1"][2], res["0"][2], "bf16", "dW1")
