@@ -38,6 +38,7 @@ _PROTOS = {
     "acm_nll_log_softmax": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _i64, _vp],
     "acm_set_l2_fetch_granularity": [_i32],
     "acm_set_gather_mode": [_i32],
+    "acm_set_mix_bwd_occupancy": [_i32],
     "acm_gemm_ab": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "acm_gemm_atb": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp],
     "acm_spmm_agg_first": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
@@ -75,6 +76,9 @@ def load():
         g = os.environ.get("ACMB200_GATHER")
         if g is not None:
             lib.acm_set_gather_mode(1 if g.lower() in ("1", "async", "cp.async") else 0)
+        o = os.environ.get("ACMB200_MIXBWD_OCC")
+        if o is not None:
+            lib.acm_set_mix_bwd_occupancy(int(o))
         _lib = lib
     return _lib
 

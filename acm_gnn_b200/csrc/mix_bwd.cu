@@ -34,8 +34,11 @@ struct BwdParams {
 
 constexpr int kBwdWarps = 8;
 
-template <typename T, int FP, int MODE>
-__global__ void __launch_bounds__(kBwdWarps * 32) mix_bwd_kernel(const BwdParams p) {
+// MINB = minimum resident CTAs per SM asked of ptxas: 2 -> ~120 registers, no spills, 16 warps/SM;
+// 3 -> 80 registers with ~120 B of spills but 24 warps/SM (more rows in flight for this
+// streaming kernel).  Selected at run time (acm_set_mix_bwd_occupancy) for the plain K=3 mode.
+template <typename T, int FP, int MODE, int MINB>
+__global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const BwdParams p) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
   constexpr int RPB = RPW * kBwdWarps;
@@ -290,26 +293,37 @@ __global__ void __launch_bounds__(kBwdWarps * 32) mix_bwd_kernel(const BwdParams
   }
 }
 
+static int g_mix_bwd_minb = 2;
+
+template <typename T, int FP, int MODE, int MINB>
+static int launch_bwd_impl(const BwdParams& p, cudaStream_t st);
+
 template <typename T, int FP, int MODE>
 static int launch_bwd(const BwdParams& p, cudaStream_t st) {
+  if (MODE == 0 && g_mix_bwd_minb == 3) return launch_bwd_impl<T, FP, 0, 3>(p, st);
+  return launch_bwd_impl<T, FP, MODE, 2>(p, st);
+}
+
+template <typename T, int FP, int MODE, int MINB>
+static int launch_bwd_impl(const BwdParams& p, cudaStream_t st) {
   constexpr int LANES = FP / 8;
   constexpr int RPB = (32 / LANES) * kBwdWarps;
   int64_t blocks = (p.n_rows + RPB - 1) / RPB;
   if (blocks == 0) return 0;
   // persistent-style grid: a few CTAs per SM, grid-stride over rows, so the number of
   // global atomics per parameter element stays ~ #CTAs
-  const int64_t cap = 148 * (MODE ? 2 : 4);
+  const int64_t cap = 148 * (MODE ? 2 : (MINB == 3 ? 6 : 4));
   if (blocks > cap) blocks = cap;
   const size_t nfl = (size_t)(MODE ? 4 : 3) * FP * 2 + 32 + (MODE ? 16 * FP + 4 : 0);
   const size_t smem = sizeof(float) * nfl;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(mix_bwd_kernel<T, FP, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mix_bwd_kernel<T, FP, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("mix_bwd: cannot raise dynamic shared memory to %zu: %s", smem, cudaGetErrorString(e));
       return (int)e;
     }
   }
-  mix_bwd_kernel<T, FP, MODE><<<(unsigned)blocks, kBwdWarps * 32, smem, st>>>(p);
+  mix_bwd_kernel<T, FP, MODE, MINB><<<(unsigned)blocks, kBwdWarps * 32, smem, st>>>(p);
   ACM_LAUNCH_CHECK("mix_bwd");
   return 0;
 }
@@ -347,5 +361,14 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
   } else {
     ACM_DISPATCH_FP(fp, return mode ? launch_bwd<float, FP, 1>(p, st) : launch_bwd<float, FP, 0>(p, st));
   }
+  return 0;
+}
+
+extern "C" int acm_set_mix_bwd_occupancy(int min_blocks_per_sm) {
+  if (min_blocks_per_sm != 2 && min_blocks_per_sm != 3) {
+    acm::set_error("mix_bwd occupancy must be 2 or 3 CTAs per SM");
+    return ACM_ERR_BAD_ARG;
+  }
+  acm::g_mix_bwd_minb = min_blocks_per_sm;
   return 0;
 }

@@ -155,6 +155,10 @@ int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
                      void* y, int y_dtype, int64_t ldy, void* o_save, float* att, float* sig,
                      const int32_t* long_rows, int n_long, const float* long_acc, void* stream);
 
+/* Register/occupancy trade-off of mix_bwd_kernel (plain 3-channel mode): 2 (default) or 3 resident
+ * CTAs per SM. */
+int acm_set_mix_bwd_occupancy(int min_blocks_per_sm);
+
 /* Gather implementation of acm_spmm_mix_fwd: 1 (default) = cp.async ring in shared memory (each
  * lane keeps 8 neighbour rows in flight without register staging), 0 = LDG register staging. */
 int acm_set_gather_mode(int mode);
