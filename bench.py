@@ -364,6 +364,8 @@ def run_ours(args):
     fp0 = padded_width(hid)
     s_el = 2 if args.dtype == "bf16" else 4
     nnz_loc = op.nnz
+    # bytes per element of layer 0's output Y: bf16 inter-layer activations or the fp32 boundary
+    y_el = 2 if getattr(model.gcns[0], "acm_out_dtype", "fp32") == "bf16" and args.dtype == "bf16" else 4
     fpx = padded_width(fin) if fin <= 256 else 0
     key_agg = f"acm_spmm_agg_first:{fpx}"
     if key_agg in summ:
@@ -374,7 +376,7 @@ def run_ours(args):
     else:
         key = f"acm_spmm_mix_fwd:{fp0}"
         kname = "spmm_mix_fwd_kernel (fused aggregation+attention+mix, layer 0)"
-        alg_bytes = nnz_loc * (2 * fp0 * s_el + 4) + n_loc * (fp0 * s_el + hid * 4 + 8) + n_loc * (2 * fp0 * s_el + 12)
+        alg_bytes = nnz_loc * (2 * fp0 * s_el + 4) + n_loc * (fp0 * s_el + hid * y_el + 8) + n_loc * (2 * fp0 * s_el + 12)
     roof = None
     if key in summ:
         cnt, ms = summ[key]
@@ -422,7 +424,7 @@ def run_ours(args):
         kf = f"acm_spmm_mix_fwd:{fp0}"
         if kf in s_ns:
             cnt, ms = s_ns[kf]
-            ab = nnz_loc * (2 * fp0 * s_el + 4) + n_loc * (fp0 * s_el + hid * 4 + 8) + n_loc * (2 * fp0 * s_el + 12)
+            ab = nnz_loc * (2 * fp0 * s_el + 4) + n_loc * (fp0 * s_el + hid * y_el + 8) + n_loc * (2 * fp0 * s_el + 12)
             ach = ab / (ms / cnt * 1e-3) / 1e9
             tr = None
             try:
