@@ -39,6 +39,7 @@ _PROTOS = {
     "acm_set_l2_fetch_granularity": [_i32],
     "acm_set_gather_mode": [_i32],
     "acm_set_mix_bwd_occupancy": [_i32],
+    "acm_set_mix_bwd_ring": [_i32],
     "acm_gemm_ab": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "acm_gemm_atb": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp],
     "acm_spmm_agg_first": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
@@ -76,6 +77,9 @@ def load():
         g = os.environ.get("ACMB200_GATHER")
         if g is not None:
             lib.acm_set_gather_mode(1 if g.lower() in ("1", "async", "cp.async") else 0)
+        r = os.environ.get("ACMB200_MIXBWD_RING")
+        if r is not None:
+            lib.acm_set_mix_bwd_ring(int(r))
         o = os.environ.get("ACMB200_MIXBWD_OCC")
         if o is not None:
             lib.acm_set_mix_bwd_occupancy(int(o))

@@ -23,7 +23,7 @@ struct BwdParams {
   const float* att;
   const float* sig;
   const float* pack;
-  int k, ln, variant, f, vec_g, g_bf16;
+  int k, ln, variant, f, vec_g, g_bf16, ring;
   float out_scale;
   void* t_lh;
   void* dh_all;
@@ -33,6 +33,21 @@ struct BwdParams {
 };
 
 constexpr int kBwdWarps = 8;
+
+// cp.async ring for the streaming inputs (bf16 tables, plain 3-channel mode): every lane prefetches
+// its own slices of G, O_L, O_H and HI for the next kRingStages-1 rows of its lane group straight
+// into shared memory, so ~4 rows per group are in flight instead of the one row that the 120
+// registers of this kernel leave room for.
+constexpr int kRingStages = 4;
+constexpr int kRingStageBytes = 32 * (32 + 3 * 16);   // per warp: G (<=32 B/lane) | O_L | O_H | HI (16 B/lane each)
+
+__device__ __forceinline__ void bwd_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void bwd_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bwd_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // MINB = minimum resident CTAs per SM asked of ptxas: 2 -> ~120 registers, no spills, 16 warps/SM;
 // 3 -> 80 registers with ~120 B of spills but 24 warps/SM (more rows in flight for this
@@ -107,8 +122,49 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
 #pragma unroll
   for (int i = 0; i < 16; ++i) dav[i] = 0.f;
 
-  for (int64_t base = (int64_t)blockIdx.x * RPB; base < p.n_rows; base += (int64_t)gridDim.x * RPB) {
-    const int64_t row = base + warp * RPW + sub;
+  constexpr bool RING_OK = (MODE == 0) && (sizeof(T) == 2);
+  const bool ring = RING_OK && p.ring;
+  const int64_t stride = (int64_t)gridDim.x * RPB;
+  const int64_t base0 = (int64_t)blockIdx.x * RPB;
+  const int64_t n_iter = base0 < p.n_rows ? (p.n_rows - base0 + stride - 1) / stride : 0;
+  uint8_t* ring_w = nullptr;
+  uint32_t ring_u32 = 0;
+  auto ring_issue = [&](int64_t r, int slot) {
+    const uint32_t d = ring_u32 + slot * kRingStageBytes;
+    if (p.g_bf16) {
+      bwd_cp_async16(d + lane * 32, reinterpret_cast<const __nv_bfloat16*>(p.g) + r * p.ldg + f0);
+    } else {
+      const float* gr = p.g + r * p.ldg + f0;
+      bwd_cp_async16(d + lane * 32, gr);
+      bwd_cp_async16(d + lane * 32 + 16, gr + 4);
+    }
+    const T* ol = reinterpret_cast<const T*>(p.o_lh) + r * TW + f0;
+    bwd_cp_async16(d + 1024 + lane * 16, ol);
+    bwd_cp_async16(d + 1536 + lane * 16, ol + FP);
+    bwd_cp_async16(d + 2048 + lane * 16, reinterpret_cast<const T*>(p.h_i) + r * FP + f0);
+  };
+  if (ring) {
+    // the ring follows the parameter / reduction arrays in dynamic shared memory
+    constexpr int kFloats = KMAX * FP * 2 + 32;
+    ring_w = reinterpret_cast<uint8_t*>(smem + ((kFloats + 3) & ~3)) + warp * (kRingStages * kRingStageBytes);
+    ring_u32 = (uint32_t)__cvta_generic_to_shared(ring_w);
+#pragma unroll
+    for (int st = 0; st < kRingStages; ++st) {
+      const int64_t r = base0 + st * stride + warp * RPW + sub;
+      if (st < n_iter && r < p.n_rows) ring_issue(r, st);
+      bwd_cp_async_commit();
+    }
+  }
+  // staging tile of the narrow-row peer push: behind the base arrays and the (optional) ring
+  T* push_stage = nullptr;
+  if (p.peers.n > 0 && LANES < 32) {
+    constexpr int kBaseFloats = (MODE ? 4 : 3) * FP * 2 + 32 + (MODE ? 16 * FP + 4 : 0);
+    uint8_t* b = reinterpret_cast<uint8_t*>(smem + ((kBaseFloats + 3) & ~3));
+    if (ring) b += kBwdWarps * kRingStages * kRingStageBytes;
+    push_stage = reinterpret_cast<T*>(b);
+  }
+  for (int64_t it = 0; it < n_iter; ++it) {
+    const int64_t row = base0 + it * stride + warp * RPW + sub;
     const bool valid = row < p.n_rows;
     float G[8], o[KMAX][8], al[KMAX], sg[KMAX];
 #pragma unroll
@@ -120,7 +176,34 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
 #pragma unroll
       for (int t = 0; t < 8; ++t) o[k][t] = 0.f;
     }
-    if (valid) {
+    if (ring) {
+      bwd_cp_async_wait<kRingStages - 1>();
+      const int slot = (int)(it & (kRingStages - 1));
+      if (valid) {
+        const uint8_t* d = ring_w + slot * kRingStageBytes;
+        if (p.g_bf16) {
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(d + lane * 32), G);
+        } else {
+          const float4 a = *reinterpret_cast<const float4*>(d + lane * 32);
+          const float4 b = *reinterpret_cast<const float4*>(d + lane * 32 + 16);
+          G[0] = a.x; G[1] = a.y; G[2] = a.z; G[3] = a.w;
+          G[4] = b.x; G[5] = b.y; G[6] = b.z; G[7] = b.w;
+        }
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(d + 1024 + lane * 16), o[0]);
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(d + 1536 + lane * 16), o[1]);
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(d + 2048 + lane * 16), o[2]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[2][t] = fmaxf(o[2][t], 0.f);
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          al[k] = __ldg(p.att + row * K + k);
+          sg[k] = __ldg(p.sig + row * K + k);
+        }
+      }
+      const int64_t rn = base0 + (it + kRingStages) * stride + warp * RPW + sub;
+      if (it + kRingStages < n_iter && rn < p.n_rows) ring_issue(rn, slot);
+      bwd_cp_async_commit();
+    } else if (valid) {
       const float* gr = p.g + row * p.ldg + f0;
       if (p.g_bf16) {
         const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(p.g) + row * p.ldg + f0;
@@ -234,10 +317,42 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
         }
       }
     }
+    if (p.peers.n > 0 && LANES < 32) {
+      // fused all-gather, narrow rows: a lane's 16-byte slices of one row are only 32..256 B apart
+      // from the next lane group's, which would reach NVLink as small fragments.  The warp's RPW
+      // consecutive rows (512*sizeof(T) bytes) are staged in shared memory and pushed to every
+      // peer as fully contiguous 512-byte warp stores.
+      T* stg = push_stage + warp * (RPW * TW);
+      if (valid) {
+        float out[8];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) out[t] = (p.variant || o[k][t] > 0.f) ? dO[k][t] : 0.f;
+          Slice8<T>::store(stg + sub * TW + k * FP + f0, out);
+        }
+      }
+      __syncwarp();
+      const int64_t first_row = base0 + it * stride + warp * RPW;
+      int64_t rows_valid = p.n_rows - first_row;
+      if (rows_valid > RPW) rows_valid = RPW;
+      if (rows_valid > 0) {
+        const int n_vec = (int)(rows_valid * TW * sizeof(T) / 16);
+        const uint4* src = reinterpret_cast<const uint4*>(stg);
+        const int64_t off = (p.peers.row_off + first_row) * TW;
+#pragma unroll 1
+        for (int r = 0; r < p.peers.n; ++r) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.peers.tables[r]) + off);
+          for (int v = lane; v < n_vec; v += 32) dst[v] = src[v];
+        }
+      }
+      __syncwarp();
+    }
     if (valid) {
       float out[8];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
+        if (p.peers.n > 0 && LANES < 32) break;
 #pragma unroll
         for (int t = 0; t < 8; ++t) out[t] = (p.variant || o[k][t] > 0.f) ? dO[k][t] : 0.f;
         if (p.peers.n > 0) {
@@ -294,6 +409,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
 }
 
 static int g_mix_bwd_minb = 2;
+static int g_mix_bwd_ring = 1;
 
 template <typename T, int FP, int MODE, int MINB>
 static int launch_bwd_impl(const BwdParams& p, cudaStream_t st);
@@ -315,7 +431,9 @@ static int launch_bwd_impl(const BwdParams& p, cudaStream_t st) {
   const int64_t cap = 148 * (MODE ? 2 : (MINB == 3 ? 6 : 4));
   if (blocks > cap) blocks = cap;
   const size_t nfl = (size_t)(MODE ? 4 : 3) * FP * 2 + 32 + (MODE ? 16 * FP + 4 : 0);
-  const size_t smem = sizeof(float) * nfl;
+  size_t smem = sizeof(float) * ((nfl + 3) & ~(size_t)3);
+  if (MODE == 0 && sizeof(T) == 2 && p.ring) smem += (size_t)kBwdWarps * kRingStages * kRingStageBytes;
+  if (p.peers.n > 0 && LANES < 32) smem += (size_t)kBwdWarps * 512 * sizeof(T);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mix_bwd_kernel<T, FP, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -352,6 +470,10 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
   p.peers = PeerTables{};
   p.peers.n = n_peers; p.peers.row_off = peer_row_off;
   for (int r = 0; r < n_peers; ++r) p.peers.tables[r] = peer_tables[r];
+  // cp.async ring: needs 16-byte aligned, unpadded rows (f == fp) of every streamed input
+  p.ring = (k_channels == 3 && !ln_live && f == fp && (ldg % 8 == 0 || (!(g_dtype == ACM_BF16) && ldg % 4 == 0)) &&
+            ((reinterpret_cast<uintptr_t>(g) & 15) == 0) && ((reinterpret_cast<uintptr_t>(o_lh) & 15) == 0) &&
+            ((reinterpret_cast<uintptr_t>(h_i) & 15) == 0)) ? g_mix_bwd_ring : 0;
   p.vec_g = p.g_bf16 ? ((f % 8 == 0) && (ldg % 8 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0))
                      : ((f % 4 == 0) && (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -361,6 +483,11 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
   } else {
     ACM_DISPATCH_FP(fp, return mode ? launch_bwd<float, FP, 1>(p, st) : launch_bwd<float, FP, 0>(p, st));
   }
+  return 0;
+}
+
+extern "C" int acm_set_mix_bwd_ring(int on) {
+  acm::g_mix_bwd_ring = on ? 1 : 0;
   return 0;
 }
 

@@ -76,9 +76,17 @@ class RowPartition:
         return self._push_ok
 
     def symm_table(self, key, width, dtype, device):
-        """Persistent [world*rows_per_rank, width] table in symmetric memory, one per (layer,
-        direction).  Returns (tensor, handle, ctypes array of the ``world`` peer base pointers)."""
-        k = (key, width, dtype)
+        """Persistent [world*rows_per_rank, width] table in symmetric memory, TWO per (layer,
+        direction), used alternately.  Returns (tensor, handle, ctypes array of the ``world``
+        peer base pointers).
+
+        Alternating buffers removes the "everybody is done reading" barrier before a push: a
+        buffer is rewritten two uses later, and by then every rank has passed the post-push
+        barrier of the use in between, which it can only reach after finishing its reads of this
+        buffer (stream order)."""
+        par = self._symm.get(("parity", key), 0)
+        self._symm[("parity", key)] = par ^ 1
+        k = (key, par, width, dtype)
         hit = self._symm.get(k)
         if hit is not None:
             return hit

@@ -274,12 +274,12 @@ class AcmLayerFunction(torch.autograd.Function):
             push = cfg.dist is not None and impl == _lib.GEMM_TCGEN05 and cfg.dist.push_enabled()
             if push:
                 # fused GEMM + all-gather: the epilogue stores every finished [HL|HH] row into all
-                # ranks' tables through NVLink peer mappings; barriers order reuse of the table
+                # ranks' tables through NVLink peer mappings; one device-side barrier afterwards
+                # (tables alternate between two buffers, see RowPartition.symm_table)
                 table, hdl, ptrs = cfg.dist.symm_table((cfg.layer_key, "fwd"), 2 * fp, tdt, dev)
-                hdl.barrier(channel=0)     # every rank is done reading the previous contents
                 _lib.call("acm_gemm_xw_fwd_push", xs.data_ptr(), ldx, wcat_t.data_ptr(), ctypes.addressof(ptrs),
                           cfg.dist.world, op.row0, h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
-                hdl.barrier(channel=1)     # every rank's rows have landed everywhere
+                hdl.barrier(channel=0)     # every rank's rows have landed everywhere
                 h_lh = table[op.row0:op.row0 + n]
             else:
                 h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
@@ -353,12 +353,11 @@ class AcmLayerFunction(torch.autograd.Function):
         if push:
             # fused mix_bwd + all-gather of the backward operand table (peer stores over NVLink)
             t_table, hdl, ptrs = cfg.dist.symm_table((cfg.layer_key, "bwd"), 2 * fp, tdt, dev)
-            hdl.barrier(channel=0)
             _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), gdt, f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
                       att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
                       float(cfg.out_scale), 0, dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
                       ctypes.addressof(ptrs), cfg.dist.world, op.row0, st, tag=fp)
-            hdl.barrier(channel=1)
+            hdl.barrier(channel=0)
             t_lh = None
         else:
             t_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)

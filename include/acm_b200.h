@@ -158,6 +158,8 @@ int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
 /* Register/occupancy trade-off of mix_bwd_kernel (plain 3-channel mode): 2 (default) or 3 resident
  * CTAs per SM. */
 int acm_set_mix_bwd_occupancy(int min_blocks_per_sm);
+/* cp.async shared-memory ring for the streamed inputs of mix_bwd_kernel (bf16 tables): 1 on (default), 0 off. */
+int acm_set_mix_bwd_ring(int on);
 
 /* Gather implementation of acm_spmm_mix_fwd: 1 (default) = cp.async ring in shared memory (each
  * lane keeps 8 neighbour rows in flight without register staging), 0 = LDG register staging. */
