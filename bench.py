@@ -50,6 +50,11 @@ def parse_args():
     ap.add_argument("--torch-loss", action="store_true",
                     help="use the reference's torch glue (log_softmax + index + nll_loss) instead of the fused loss kernel")
     ap.add_argument("--l2-fetch", type=int, default=0, help="cudaLimitMaxL2FetchGranularity (0 = leave default)")
+    ap.add_argument("--model-type", default="acmgcn", choices=["acmgcn", "acmgcnp", "acmgcnpp"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--flavour", default="pytorch", choices=["pytorch", "geometric"],
+                    help="geometric: LayerNorm of the attention logits is live for acmgcnp/acmgcnpp (quirk Q1)")
+    ap.add_argument("--structure-info", type=int, default=0)
     ap.add_argument("--skew", type=float, default=0.0,
                     help="degree-skewed variant of the synthetic graph (SURVEY 8d): destination = N*u^skew, u~U(0,1), "
                          "ids randomly permuted; 0 = uniform endpoints (the headline workload)")
@@ -200,7 +205,9 @@ def run_reference(args):
 
 def workload_config(args, world):
     return {"workload": f"synthetic uniform random graph N={args.nodes} E={args.edges} (+N self loops), Fin={args.fin} "
-                        f"hidden={args.hidden} classes={args.nclass}, 2-layer acmgcn variant 0 dropout 0 (SURVEY 8d cfg 5)",
+                        f"hidden={args.hidden} classes={args.nclass}, 2-layer {args.model_type} variant {args.variant} "
+                        f"structure_info {args.structure_info} ({args.flavour} flavour) dropout 0"
+                        + (" (SURVEY 8d cfg 5)" if args.nodes == 10_000_000 else ""),
             "skew": args.skew, "nodes": args.nodes, "edges": args.edges, "fin": args.fin, "hidden": args.hidden, "nclass": args.nclass,
             "step": "forward + log_softmax/NLL (" + ("torch glue" if args.torch_loss else "fused acm_nll_log_softmax") + ") + backward + Adam.step",
             "partition": f"1-D row partition over {world} GPU(s), NCCL all-gather of the operand table" if world > 1 else "single GPU",
@@ -246,7 +253,7 @@ def run_ours(args):
 
     # ---- inputs, resident in HBM before the timed region -------------------------------------
     row, col = synthetic_graph_gpu(n, args.edges, dev, seed=0, skew=args.skew)
-    op_full = A.AcmOperator.from_edges(row, col, n, "pytorch")
+    op_full = A.AcmOperator.from_edges(row, col, n, args.flavour, with_raw=bool(args.structure_info))
     del row, col
     nnz_global = op_full.nnz
     max_deg = int((op_full.low.rowptr[1:] - op_full.low.rowptr[:-1]).max().item())
@@ -275,7 +282,8 @@ def run_ours(args):
     n_train_global = float(n_train.item())
 
     torch.manual_seed(42)  # identical replicated parameters on every rank
-    model = A.GCN(fin, hid, ncls, 2, n, 0.0, "acmgcn", 0, variant=False).to(dev)
+    model = A.GCN(fin, hid, ncls, 2, n, 0.0, args.model_type, args.structure_info, variant=bool(args.variant),
+                  flavour=args.flavour).to(dev)
     if part is not None:
         attach(model, part)
     params = [p for k, p in model.named_parameters() if k not in ("fea_param", "xX_param")]
