@@ -24,6 +24,8 @@ _PROTOS = {
     "acm_csr_rowptr": [_vp, _i64, _i64, _vp, _vp],
     "acm_degree_normalise": [_vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "acm_csr_transpose_values": [_vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "acm_pack_params": [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "acm_unpack_grads": [_i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "acm_cast_pad": [_vp, _i64, _i64, _i64, _vp, _i32, _i64, _vp],
     "acm_gemm_xw_fwd": [_i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
     "acm_gemm_bwd_dw": [_i32, _i32, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _vp],

@@ -5,10 +5,18 @@
 //   d_O_k = c alpha_k G + d_z_k a_k   (through LayerNorm backward when it is live)
 //   d_a_k += O_k^T d_z_k   (LayerNorm(O_k) when live; plus d_gamma, d_beta)
 //   variant 0: d_S_k = d_O_k * [O_k > 0]          variant 1: d_S_k = d_O_k
-// Same lane mapping as the forward kernel (LANES = FP/8 lanes per row, 8 features per
-// lane), no gather: pure streaming, HBM bound.  Parameter gradients are accumulated in
-// registers over a grid-stride loop, reduced through shared memory and flushed with one
-// global atomicAdd per element per block.
+// Same lane mapping as the forward kernel (LANES = FP/8 lanes per row, 8 features per lane), no
+// gather: pure streaming, HBM bound.  Parameter gradients are accumulated in registers over a
+// grid-stride loop, reduced through shared memory and flushed with one global atomicAdd per
+// element per block.
+//
+// LayerNorm (ACM-Geometric flavour): with xhat = (O - mu)/sigma, y = gamma xhat + beta, z = y.a
+// the three per-feature parameter gradients need only ONE accumulator T_k[f] = sum_i dz_k,i xhat_i,f
+// and one scalar S_k = sum_i dz_k,i per channel:
+//   d_a_k[f] = gamma_f T_k[f] + beta_f S_k ;  d_gamma_k[f] = a_f T_k[f] ;  d_beta_k[f] = a_f S_k
+// so the LayerNorm mode costs the same registers as the plain mode.
+//
+// MODE bit 0: LayerNorm live; bit 1: 4 channels (structure channel).
 #include "acm_common.cuh"
 
 namespace acm {
@@ -34,10 +42,10 @@ struct BwdParams {
 
 constexpr int kBwdWarps = 8;
 
-// cp.async ring for the streaming inputs (bf16 tables, plain 3-channel mode): every lane prefetches
+// cp.async ring for the streaming inputs (bf16 tables, 3-channel modes): every lane prefetches
 // its own slices of G, O_L, O_H and HI for the next kRingStages-1 rows of its lane group straight
-// into shared memory, so ~4 rows per group are in flight instead of the one row that the 120
-// registers of this kernel leave room for.
+// into shared memory, so ~4 rows per group are in flight instead of the one row that the ~125
+// registers of this kernel leave room for (measured 9.8 -> 7.7 ms at the headline config).
 constexpr int kRingStages = 4;
 constexpr int kRingStageBytes = 32 * (32 + 3 * 16);   // per warp: G (<=32 B/lane) | O_L | O_H | HI (16 B/lane each)
 
@@ -49,55 +57,62 @@ template <int N> __device__ __forceinline__ void bwd_cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// MINB = minimum resident CTAs per SM asked of ptxas: 2 -> ~120 registers, no spills, 16 warps/SM;
-// 3 -> 80 registers with ~120 B of spills but 24 warps/SM (more rows in flight for this
-// streaming kernel).  Selected at run time (acm_set_mix_bwd_occupancy) for the plain K=3 mode.
+template <int FP, int MODE>
+struct BwdSmem {
+  static constexpr bool LN = (MODE & 1) != 0;
+  static constexpr int KMAX = (MODE & 2) ? 4 : 3;
+  // s_a [KMAX][FP] | s_avec [16] | s_dav [16] | s_da [KMAX][FP] | LN: gamma, beta [KMAX][FP] each | sums [16]
+  static constexpr int kFloats = KMAX * FP * 2 + 32 + (LN ? 2 * KMAX * FP : 0) + 16;
+  static constexpr int kFloatsPadded = (kFloats + 3) & ~3;
+};
+
+// MINB = minimum resident CTAs per SM asked of ptxas (2: ~125 registers, no spills)
 template <typename T, int FP, int MODE, int MINB>
 __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const BwdParams p) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
   constexpr int RPB = RPW * kBwdWarps;
-  constexpr int KMAX = MODE ? 4 : 3;
+  constexpr bool LN = (MODE & 1) != 0;
+  constexpr bool K4 = (MODE & 2) != 0;
+  constexpr int KMAX = K4 ? 4 : 3;
+  constexpr int K = KMAX;
   constexpr int TW = 2 * FP;
+  using SM = BwdSmem<FP, MODE>;
 
   extern __shared__ float smem[];
-  float* s_a = smem;                          // [KMAX][FP]
-  float* s_avec = s_a + KMAX * FP;            // [16]
-  float* s_dav = s_avec + 16;                 // [16]  d att_vec
-  float* s_da = s_dav + 16;                   // [KMAX][FP]  d a_k
-  float* s_gam = s_da + KMAX * FP;            // MODE1: gamma [4][FP]
-  float* s_bet = s_gam + (MODE ? 4 * FP : 0); // MODE1: beta  [4][FP]
-  float* s_dg = s_bet + (MODE ? 4 * FP : 0);  // MODE1: d gamma [4][FP]
-  float* s_db = s_dg + (MODE ? 4 * FP : 0);   // MODE1: d beta  [4][FP]
-  float* s_sga = s_db + (MODE ? 4 * FP : 0);  // MODE1: [4] sum_f gamma*a
+  float* s_a = smem;                            // [KMAX][FP]
+  float* s_avec = s_a + KMAX * FP;              // [16]
+  float* s_dav = s_avec + 16;                   // [16]  d att_vec
+  float* s_da = s_dav + 16;                     // [KMAX][FP]  d a_k  (LN: T_k)
+  float* s_gam = s_da + KMAX * FP;              // LN: gamma [KMAX][FP]
+  float* s_bet = s_gam + (LN ? KMAX * FP : 0);  // LN: beta  [KMAX][FP]
+  float* s_sum = s_bet + (LN ? KMAX * FP : 0);  // [0..4) sum_f gamma*a ; [4..8) S_k = sum_i dz_k,i
 
-  const int K = MODE ? p.k : 3;
-  const bool ln = MODE && p.ln;
   for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) {
     s_a[i] = p.pack[i];
     s_da[i] = 0.f;
+    if (LN) {
+      s_gam[i] = p.pack[pack_off_gamma(FP, 0) + i];
+      s_bet[i] = p.pack[pack_off_beta(FP, 0) + i];
+    }
   }
   if (threadIdx.x < 16) {
     s_avec[threadIdx.x] = p.pack[pack_off_avec(FP) + threadIdx.x];
     s_dav[threadIdx.x] = 0.f;
-  }
-  if (MODE) {
-    for (int i = threadIdx.x; i < 4 * FP; i += blockDim.x) {
-      s_gam[i] = p.pack[pack_off_gamma(FP, 0) + i];
-      s_bet[i] = p.pack[pack_off_beta(FP, 0) + i];
-      s_dg[i] = 0.f;
-      s_db[i] = 0.f;
-    }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (w < 4) {
-      float sg = 0.f;
-      for (int i = l; i < FP; i += 32) sg += p.pack[pack_off_gamma(FP, w) + i] * p.pack[pack_off_a(FP, w) + i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);
-      if (l == 0) s_sga[w] = sg;
-    }
+    s_sum[threadIdx.x] = 0.f;
   }
   __syncthreads();
+  if (LN) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (w < KMAX) {
+      float sg = 0.f;
+      for (int i = l; i < FP; i += 32) sg += s_gam[w * FP + i] * s_a[w * FP + i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      if (l == 0) s_sum[w] = sg;
+    }
+    __syncthreads();
+  }
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -108,21 +123,19 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
   const float inv_k = 1.f / (float)K;
   const float inv_f = 1.f / (float)p.f;
 
-  float da[KMAX][8];
-  float dgm[MODE ? 4 : 1][8], dbt[MODE ? 4 : 1][8];
+  float da[KMAX][8];     // plain: sum_i dz O ; LN: T_k = sum_i dz xhat
+  float dsum[KMAX];      // LN: S_k = sum_i dz_k,i (identical on every lane of a group)
   float dav[16];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k)
+  for (int k = 0; k < KMAX; ++k) {
+    dsum[k] = 0.f;
 #pragma unroll
     for (int t = 0; t < 8; ++t) da[k][t] = 0.f;
-#pragma unroll
-  for (int k = 0; k < (MODE ? 4 : 1); ++k)
-#pragma unroll
-    for (int t = 0; t < 8; ++t) dgm[k][t] = dbt[k][t] = 0.f;
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) dav[i] = 0.f;
 
-  constexpr bool RING_OK = (MODE == 0) && (sizeof(T) == 2);
+  constexpr bool RING_OK = !K4 && (sizeof(T) == 2);
   const bool ring = RING_OK && p.ring;
   const int64_t stride = (int64_t)gridDim.x * RPB;
   const int64_t base0 = (int64_t)blockIdx.x * RPB;
@@ -143,11 +156,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
     bwd_cp_async16(d + 1536 + lane * 16, ol + FP);
     bwd_cp_async16(d + 2048 + lane * 16, reinterpret_cast<const T*>(p.h_i) + r * FP + f0);
   };
+  uint8_t* tail = reinterpret_cast<uint8_t*>(smem + SM::kFloatsPadded);  // ring, then push staging
   if (ring) {
-    // the ring follows the parameter / reduction arrays in dynamic shared memory
-    constexpr int kFloats = KMAX * FP * 2 + 32;
-    ring_w = reinterpret_cast<uint8_t*>(smem + ((kFloats + 3) & ~3)) + warp * (kRingStages * kRingStageBytes);
+    ring_w = tail + warp * (kRingStages * kRingStageBytes);
     ring_u32 = (uint32_t)__cvta_generic_to_shared(ring_w);
+    tail += kBwdWarps * kRingStages * kRingStageBytes;
 #pragma unroll
     for (int st = 0; st < kRingStages; ++st) {
       const int64_t r = base0 + st * stride + warp * RPW + sub;
@@ -155,14 +168,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
       bwd_cp_async_commit();
     }
   }
-  // staging tile of the narrow-row peer push: behind the base arrays and the (optional) ring
-  T* push_stage = nullptr;
-  if (p.peers.n > 0 && LANES < 32) {
-    constexpr int kBaseFloats = (MODE ? 4 : 3) * FP * 2 + 32 + (MODE ? 16 * FP + 4 : 0);
-    uint8_t* b = reinterpret_cast<uint8_t*>(smem + ((kBaseFloats + 3) & ~3));
-    if (ring) b += kBwdWarps * kRingStages * kRingStageBytes;
-    push_stage = reinterpret_cast<T*>(b);
-  }
+  // staging tile of the narrow-row peer push
+  T* push_stage = (p.peers.n > 0 && LANES < 32) ? reinterpret_cast<T*>(tail) : nullptr;
+
   for (int64_t it = 0; it < n_iter; ++it) {
     const int64_t row = base0 + it * stride + warp * RPW + sub;
     const bool valid = row < p.n_rows;
@@ -192,13 +200,6 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
         unpack_bf16x8(*reinterpret_cast<const uint4*>(d + 1024 + lane * 16), o[0]);
         unpack_bf16x8(*reinterpret_cast<const uint4*>(d + 1536 + lane * 16), o[1]);
         unpack_bf16x8(*reinterpret_cast<const uint4*>(d + 2048 + lane * 16), o[2]);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) o[2][t] = fmaxf(o[2][t], 0.f);
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-          al[k] = __ldg(p.att + row * K + k);
-          sg[k] = __ldg(p.sig + row * K + k);
-        }
       }
       const int64_t rn = base0 + (it + kRingStages) * stride + warp * RPW + sub;
       if (it + kRingStages < n_iter && rn < p.n_rows) ring_issue(rn, slot);
@@ -233,19 +234,20 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
       a.to_float(o[0]);
       b.to_float(o[1]);
       d.to_float(o[2]);
+    }
+    if (valid) {
 #pragma unroll
       for (int t = 0; t < 8; ++t) o[2][t] = fmaxf(o[2][t], 0.f);
-      if (MODE && K == 4) {
+      if (K4) {
         Slice8<T> s4;
         s4.load(reinterpret_cast<const T*>(p.o_s) + row * FP + f0);
         s4.to_float(o[KMAX - 1]);
       }
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) {
-          al[k] = __ldg(p.att + row * K + k);
-          sg[k] = __ldg(p.sig + row * K + k);
-        }
+      for (int k = 0; k < KMAX; ++k) {
+        al[k] = __ldg(p.att + row * K + k);
+        sg[k] = __ldg(p.sig + row * K + k);
+      }
     }
     // d_alpha
     float dal[KMAX], dlog[KMAX], dz[KMAX];
@@ -264,10 +266,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
     for (int j = 0; j < KMAX; ++j) {
       float ds = 0.f;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) ds = fmaf(dlog[k], s_avec[j * 4 + k], ds);
+      for (int k = 0; k < KMAX; ++k) ds = fmaf(dlog[k], s_avec[j * 4 + k], ds);
       ds *= inv_k;
-      dz[j] = (j < K) ? ds * sg[j] * (1.f - sg[j]) : 0.f;
+      dz[j] = ds * sg[j] * (1.f - sg[j]);
       if (gl == 0 && valid) {
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) dav[j * 4 + k] = fmaf(sg[j], dlog[k] * inv_k, dav[j * 4 + k]);
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
     float dO[KMAX][8];
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-      if (!ln) {
+      if (!LN) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           da[k][t] = fmaf(dz[k], o[k][t], da[k][t]);
@@ -301,18 +302,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
           xh[t] *= rstd;
           gx = fmaf(s_gam[k * FP + f0 + t] * s_a[k * FP + f0 + t], xh[t], gx);
         }
-        const float m1 = dz[k] * s_sga[k] * inv_f;
+        const float m1 = dz[k] * s_sum[k] * inv_f;
         const float m2 = dz[k] * group_sum<LANES>(gx) * inv_f;
+        dsum[k] += dz[k];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          const float av = s_a[k * FP + f0 + t];
-          const float gm = s_gam[k * FP + f0 + t];
-          const bool fv = (f0 + t < p.f);
-          const float yln = fv ? fmaf(xh[t], gm, s_bet[k * FP + f0 + t]) : 0.f;
-          da[k][t] = fmaf(dz[k], yln, da[k][t]);
-          dgm[MODE ? k : 0][t] = fmaf(dz[k] * av, xh[t], dgm[MODE ? k : 0][t]);
-          if (fv) dbt[MODE ? k : 0][t] = fmaf(dz[k], av, dbt[MODE ? k : 0][t]);
-          const float dln = fv ? rstd * (dz[k] * gm * av - m1 - xh[t] * m2) : 0.f;
+          const float ga = s_gam[k * FP + f0 + t] * s_a[k * FP + f0 + t];
+          da[k][t] = fmaf(dz[k], xh[t], da[k][t]);  // T_k
+          const float dln = (f0 + t < p.f) ? rstd * (dz[k] * ga - m1 - xh[t] * m2) : 0.f;
           dO[k][t] = fmaf(c * al[k], G[t], dln);
         }
       }
@@ -350,24 +347,26 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
     }
     if (valid) {
       float out[8];
+      if (!(p.peers.n > 0 && LANES < 32)) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (p.peers.n > 0 && LANES < 32) break;
+        for (int k = 0; k < 2; ++k) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) out[t] = (p.variant || o[k][t] > 0.f) ? dO[k][t] : 0.f;
-        if (p.peers.n > 0) {
-          // fused all-gather of the backward operand table (see PeerTables)
-          const int64_t off = (p.peers.row_off + row) * TW + f0 + k * FP;
+          for (int t = 0; t < 8; ++t) out[t] = (p.variant || o[k][t] > 0.f) ? dO[k][t] : 0.f;
+          if (p.peers.n > 0) {
+            // fused all-gather of the backward operand table (see PeerTables): wide rows, every
+            // warp store already covers 512 contiguous bytes
+            const int64_t off = (p.peers.row_off + row) * TW + f0 + k * FP;
 #pragma unroll 1
-          for (int r = 0; r < p.peers.n; ++r) Slice8<T>::store(reinterpret_cast<T*>(p.peers.tables[r]) + off, out);
-        } else {
-          Slice8<T>::store(reinterpret_cast<T*>(p.t_lh) + row * TW + f0 + k * FP, out);
+            for (int r = 0; r < p.peers.n; ++r) Slice8<T>::store(reinterpret_cast<T*>(p.peers.tables[r]) + off, out);
+          } else {
+            Slice8<T>::store(reinterpret_cast<T*>(p.t_lh) + row * TW + f0 + k * FP, out);
+          }
         }
       }
 #pragma unroll
       for (int t = 0; t < 8; ++t) out[t] = (o[2][t] > 0.f) ? dO[2][t] : 0.f;
       Slice8<T>::store(reinterpret_cast<T*>(p.dh_all) + row * (3 * FP) + 2 * FP + f0, out);
-      if (MODE && K == 4) {
+      if (K4) {
 #pragma unroll
         for (int t = 0; t < 8; ++t) out[t] = (o[KMAX - 1][t] > 0.f) ? dO[KMAX - 1][t] : 0.f;
         Slice8<T>::store(reinterpret_cast<T*>(p.dos_pre) + row * FP + f0, out);
@@ -377,34 +376,34 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
 
   // ---- flush parameter gradients: registers -> shared -> one global atomic per element ----
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k)
+  for (int k = 0; k < KMAX; ++k) {
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      atomicAdd(&s_da[k * FP + f0 + t], da[k][t]);
-      if (MODE && ln) {
-        atomicAdd(&s_dg[k * FP + f0 + t], dgm[MODE ? k : 0][t]);
-        atomicAdd(&s_db[k * FP + f0 + t], dbt[MODE ? k : 0][t]);
-      }
-    }
+    for (int t = 0; t < 8; ++t) atomicAdd(&s_da[k * FP + f0 + t], da[k][t]);
+    if (LN && gl == 0) atomicAdd(&s_sum[4 + k], dsum[k]);
+  }
   if (gl == 0) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) atomicAdd(&s_dav[i], dav[i]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) {
-    const float v = s_da[i];
-    if (v != 0.f) atomicAdd(p.dpack + i, v);
+    const float tv = s_da[i];
+    if (!LN) {
+      if (tv != 0.f) atomicAdd(p.dpack + i, tv);
+    } else {
+      const int k = i / FP, fidx = i - k * FP;
+      const float sk = s_sum[4 + k];
+      const float av = s_a[i];
+      const float d_a = (fidx < p.f) ? fmaf(s_gam[i], tv, s_bet[i] * sk) : 0.f;
+      const float d_g = av * tv, d_b = av * sk;
+      if (d_a != 0.f) atomicAdd(p.dpack + i, d_a);
+      if (d_g != 0.f) atomicAdd(p.dpack + pack_off_gamma(FP, 0) + i, d_g);
+      if (d_b != 0.f) atomicAdd(p.dpack + pack_off_beta(FP, 0) + i, d_b);
+    }
   }
   if (threadIdx.x < 16) {
     const float v = s_dav[threadIdx.x];
     if (v != 0.f) atomicAdd(p.dpack + pack_off_avec(FP) + threadIdx.x, v);
-  }
-  if (MODE && ln) {
-    for (int i = threadIdx.x; i < 4 * FP; i += blockDim.x) {
-      const float v = s_dg[i], w = s_db[i];
-      if (v != 0.f) atomicAdd(p.dpack + pack_off_gamma(FP, 0) + i, v);
-      if (w != 0.f) atomicAdd(p.dpack + pack_off_beta(FP, 0) + i, w);
-    }
   }
 }
 
@@ -412,27 +411,18 @@ static int g_mix_bwd_minb = 2;
 static int g_mix_bwd_ring = 1;
 
 template <typename T, int FP, int MODE, int MINB>
-static int launch_bwd_impl(const BwdParams& p, cudaStream_t st);
-
-template <typename T, int FP, int MODE>
-static int launch_bwd(const BwdParams& p, cudaStream_t st) {
-  if (MODE == 0 && g_mix_bwd_minb == 3) return launch_bwd_impl<T, FP, 0, 3>(p, st);
-  return launch_bwd_impl<T, FP, MODE, 2>(p, st);
-}
-
-template <typename T, int FP, int MODE, int MINB>
 static int launch_bwd_impl(const BwdParams& p, cudaStream_t st) {
   constexpr int LANES = FP / 8;
   constexpr int RPB = (32 / LANES) * kBwdWarps;
+  constexpr bool K4 = (MODE & 2) != 0;
   int64_t blocks = (p.n_rows + RPB - 1) / RPB;
   if (blocks == 0) return 0;
   // persistent-style grid: a few CTAs per SM, grid-stride over rows, so the number of
   // global atomics per parameter element stays ~ #CTAs
-  const int64_t cap = 148 * (MODE ? 2 : (MINB == 3 ? 6 : 4));
+  const int64_t cap = 148 * (MINB == 3 ? 6 : 4);
   if (blocks > cap) blocks = cap;
-  const size_t nfl = (size_t)(MODE ? 4 : 3) * FP * 2 + 32 + (MODE ? 16 * FP + 4 : 0);
-  size_t smem = sizeof(float) * ((nfl + 3) & ~(size_t)3);
-  if (MODE == 0 && sizeof(T) == 2 && p.ring) smem += (size_t)kBwdWarps * kRingStages * kRingStageBytes;
+  size_t smem = sizeof(float) * BwdSmem<FP, MODE>::kFloatsPadded;
+  if (!K4 && sizeof(T) == 2 && p.ring) smem += (size_t)kBwdWarps * kRingStages * kRingStageBytes;
   if (p.peers.n > 0 && LANES < 32) smem += (size_t)kBwdWarps * 512 * sizeof(T);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mix_bwd_kernel<T, FP, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -444,6 +434,16 @@ static int launch_bwd_impl(const BwdParams& p, cudaStream_t st) {
   mix_bwd_kernel<T, FP, MODE, MINB><<<(unsigned)blocks, kBwdWarps * 32, smem, st>>>(p);
   ACM_LAUNCH_CHECK("mix_bwd");
   return 0;
+}
+
+template <typename T, int FP>
+static int launch_bwd(const BwdParams& p, int mode, cudaStream_t st) {
+  switch (mode) {
+    case 0: return g_mix_bwd_minb == 3 ? launch_bwd_impl<T, FP, 0, 3>(p, st) : launch_bwd_impl<T, FP, 0, 2>(p, st);
+    case 1: return launch_bwd_impl<T, FP, 1, 2>(p, st);
+    case 2: return launch_bwd_impl<T, FP, 2, 2>(p, st);
+    default: return launch_bwd_impl<T, FP, 3, 2>(p, st);
+  }
 }
 
 }  // namespace acm
@@ -458,30 +458,32 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
   ACM_CHECK_ARG(n_peers >= 0 && n_peers <= kMaxPeers, "mix_bwd: 0 <= n_peers <= %d", kMaxPeers);
   ACM_CHECK_ARG(n_peers == 0 || peer_tables, "mix_bwd: peer push needs peer_tables");
   ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "mix_bwd: bad dtype %d", dtype);
+  ACM_CHECK_ARG(g_dtype == ACM_F32 || g_dtype == ACM_BF16, "mix_bwd: bad g dtype %d", g_dtype);
   ACM_CHECK_ARG(k_channels == 3 || k_channels == 4, "mix_bwd: k_channels must be 3 or 4");
   ACM_CHECK_ARG(f >= 1 && f <= fp, "mix_bwd: need 1 <= f <= fp");
   ACM_CHECK_ARG(k_channels == 3 || (o_s && dos_pre), "mix_bwd: 4 channels need o_s and dos_pre");
   ACM_CHECK_ARG(g && o_lh && h_i && att && sig && pack && (t_lh || n_peers > 0) && dh_all && dpack, "mix_bwd: null pointer");
   BwdParams p;
-  ACM_CHECK_ARG(g_dtype == ACM_F32 || g_dtype == ACM_BF16, "mix_bwd: bad g dtype %d", g_dtype);
-  p.n_rows = n_rows; p.g = reinterpret_cast<const float*>(g); p.ldg = ldg; p.g_bf16 = (g_dtype == ACM_BF16); p.o_lh = o_lh; p.h_i = h_i; p.o_s = o_s; p.att = att; p.sig = sig;
+  p.n_rows = n_rows; p.g = reinterpret_cast<const float*>(g); p.ldg = ldg; p.g_bf16 = (g_dtype == ACM_BF16);
+  p.o_lh = o_lh; p.h_i = h_i; p.o_s = o_s; p.att = att; p.sig = sig;
   p.pack = pack; p.k = k_channels; p.ln = ln_live; p.variant = variant; p.f = f; p.out_scale = out_scale;
   p.t_lh = t_lh; p.dh_all = dh_all; p.dos_pre = dos_pre; p.dpack = dpack;
   p.peers = PeerTables{};
   p.peers.n = n_peers; p.peers.row_off = peer_row_off;
   for (int r = 0; r < n_peers; ++r) p.peers.tables[r] = peer_tables[r];
   // cp.async ring: needs 16-byte aligned, unpadded rows (f == fp) of every streamed input
-  p.ring = (k_channels == 3 && !ln_live && f == fp && (ldg % 8 == 0 || (!(g_dtype == ACM_BF16) && ldg % 4 == 0)) &&
-            ((reinterpret_cast<uintptr_t>(g) & 15) == 0) && ((reinterpret_cast<uintptr_t>(o_lh) & 15) == 0) &&
-            ((reinterpret_cast<uintptr_t>(h_i) & 15) == 0)) ? g_mix_bwd_ring : 0;
+  const bool g_ok = p.g_bf16 ? (ldg % 8 == 0) : (ldg % 4 == 0);
+  p.ring = (k_channels == 3 && f == fp && g_ok && ((reinterpret_cast<uintptr_t>(g) & 15) == 0) &&
+            ((reinterpret_cast<uintptr_t>(o_lh) & 15) == 0) && ((reinterpret_cast<uintptr_t>(h_i) & 15) == 0))
+               ? g_mix_bwd_ring : 0;
   p.vec_g = p.g_bf16 ? ((f % 8 == 0) && (ldg % 8 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0))
                      : ((f % 4 == 0) && (ldg % 4 == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int mode = (k_channels == 4 || ln_live) ? 1 : 0;
+  const int mode = (ln_live ? 1 : 0) | (k_channels == 4 ? 2 : 0);
   if (dtype == ACM_BF16) {
-    ACM_DISPATCH_FP(fp, return mode ? launch_bwd<__nv_bfloat16, FP, 1>(p, st) : launch_bwd<__nv_bfloat16, FP, 0>(p, st));
+    ACM_DISPATCH_FP(fp, return launch_bwd<__nv_bfloat16, FP>(p, mode, st));
   } else {
-    ACM_DISPATCH_FP(fp, return mode ? launch_bwd<float, FP, 1>(p, st) : launch_bwd<float, FP, 0>(p, st));
+    ACM_DISPATCH_FP(fp, return launch_bwd<float, FP>(p, mode, st));
   }
   return 0;
 }

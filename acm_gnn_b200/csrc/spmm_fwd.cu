@@ -63,9 +63,11 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
                                               uint8_t* s_ring) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
-  constexpr int KMAX = MODE ? 4 : 3;
+  constexpr bool LN = (MODE & 1) != 0;   // LayerNorm of the attention logits live (ACM-Geometric flavour)
+  constexpr bool K4 = (MODE & 2) != 0;   // 4th (structure) channel
+  constexpr int KMAX = K4 ? 4 : 3;
+  constexpr int K = KMAX;
   constexpr int TW = 2 * FP;  // table row width (elements)
-  const int K = MODE ? p.k : 3;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int sub = lane / LANES;
@@ -216,8 +218,8 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
       o[1][t] = sh;
       o[2][t] = fmaxf(hi[t], 0.f);
     }
-    if (MODE) {
-      if (K == 4 && valid) {
+    if (K4) {
+      if (valid) {
         Slice8<T> s4;
         s4.load(reinterpret_cast<const T*>(p.o_s) + row * FP + gl * 8);
         s4.to_float(o[KMAX - 1]);
@@ -229,7 +231,7 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
   }
 
   float z[KMAX];
-  const bool ln = MODE && p.ln;
+  constexpr bool ln = LN;
   const float inv_f = 1.f / (float)p.f;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
@@ -326,32 +328,27 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
 
 template <typename T, int FP, int MODE, bool ASYNC>
 __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdParams p) {
-  constexpr int LANES = FP / 8;
-  constexpr int RPW = 32 / LANES;
-  constexpr int KMAX = MODE ? 4 : 3;
-  constexpr int TW = 2 * FP;  // table row width (elements)
+  constexpr bool LN = (MODE & 1) != 0;
+  constexpr int KMAX = (MODE & 2) ? 4 : 3;
 
   extern __shared__ float smem[];
   float* s_a = smem;                 // [KMAX][FP]   a_k
   float* s_avec = s_a + KMAX * FP;   // [16]
-  float* s_ga = s_avec + 16;         // MODE 1: [4][FP] gamma*a
-  float* s_sc = s_ga + (MODE ? 4 * FP : 0);  // MODE 1: [8] sum(beta*a) per channel
+  float* s_ga = s_avec + 16;         // LN: [KMAX][FP] gamma*a
+  float* s_sc = s_ga + (LN ? KMAX * FP : 0);  // LN: [8] sum(beta*a) per channel
 
-  const int K = MODE ? p.k : 3;
   for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) s_a[i] = p.pack[i];
   if (threadIdx.x < 16) s_avec[threadIdx.x] = p.pack[pack_off_avec(FP) + threadIdx.x];
-  if (MODE) {
-    if (p.ln) {
-      for (int i = threadIdx.x; i < 4 * FP; i += blockDim.x)
-        s_ga[i] = p.pack[pack_off_gamma(FP, 0) + i] * p.pack[i];
-      const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-      if (w < 4) {
-        float sb = 0.f;
-        for (int i = l; i < FP; i += 32) sb += p.pack[pack_off_beta(FP, w) + i] * p.pack[pack_off_a(FP, w) + i];
+  if (LN) {
+    for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x)
+      s_ga[i] = p.pack[pack_off_gamma(FP, 0) + i] * p.pack[i];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (w < KMAX) {
+      float sb = 0.f;
+      for (int i = l; i < FP; i += 32) sb += p.pack[pack_off_beta(FP, w) + i] * p.pack[pack_off_a(FP, w) + i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        if (l == 0) s_sc[w] = sb;
-      }
+      for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+      if (l == 0) s_sc[w] = sb;
     }
   }
   __syncthreads();
@@ -366,7 +363,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
   } else {
     // gather mode: one row block per CTA; the hardware block scheduler balances the degrees
     // the cp.async ring follows the parameter pack in dynamic shared memory (16-byte aligned)
-    constexpr int kPackFloats = (MODE ? 4 : 3) * FP + 16 + (MODE ? 4 * FP + 8 : 0);
+    constexpr int kPackFloats = KMAX * FP + 16 + (LN ? KMAX * FP + 8 : 0);
     uint8_t* s_ring = reinterpret_cast<uint8_t*>(smem + ((kPackFloats + 3) & ~3));
     fwd_row_block<T, FP, MODE, ASYNC>(p, blockIdx.x, s_a, s_avec, s_ga, s_sc, s_ring);
   }
@@ -382,7 +379,8 @@ static int launch_fwd(const FwdParams& p, cudaStream_t st) {
   if (blocks == 0) return 0;
   if (p.pre_agg && blocks > 148 * 16) blocks = 148 * 16;
   ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_mix_fwd: too many rows for one launch");
-  constexpr int kPackFloats = (MODE ? 4 : 3) * FP + 16 + (MODE ? 4 * FP + 8 : 0);
+  constexpr int KMAXh = (MODE & 2) ? 4 : 3;
+  constexpr int kPackFloats = KMAXh * FP + 16 + ((MODE & 1) ? KMAXh * FP + 8 : 0);
   // the ring pays off for wide rows (FP = 256: 97 % vs 91 % of HBM peak); for narrow rows (FP = 16,
   // two lanes per row) the per-edge commit/wait overhead costs more than it hides (measured 5.4 vs
   // 4.8 ms), so they keep the register-staged LDG loop
@@ -406,6 +404,16 @@ static int launch_fwd(const FwdParams& p, cudaStream_t st) {
   }
   ACM_LAUNCH_CHECK("spmm_mix_fwd");
   return 0;
+}
+
+template <typename T, int FP>
+static int launch_fwd_mode(const FwdParams& p, int mode, cudaStream_t st) {
+  switch (mode) {
+    case 0: return launch_fwd<T, FP, 0>(p, st);
+    case 1: return launch_fwd<T, FP, 1>(p, st);
+    case 2: return launch_fwd<T, FP, 2>(p, st);
+    default: return launch_fwd<T, FP, 3>(p, st);
+  }
 }
 
 }  // namespace acm
@@ -436,11 +444,11 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
   p.vec_y = p.y_bf16 ? ((f % 8 == 0) && (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0))
                      : ((f % 4 == 0) && (ldy % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int mode = (k_channels == 4 || ln_live) ? 1 : 0;
+  const int mode = (ln_live ? 1 : 0) | (k_channels == 4 ? 2 : 0);
   if (dtype == ACM_BF16) {
-    ACM_DISPATCH_FP(fp, return mode ? launch_fwd<__nv_bfloat16, FP, 1>(p, st) : launch_fwd<__nv_bfloat16, FP, 0>(p, st));
+    ACM_DISPATCH_FP(fp, return launch_fwd_mode<__nv_bfloat16, FP>(p, mode, st));
   } else {
-    ACM_DISPATCH_FP(fp, return mode ? launch_fwd<float, FP, 1>(p, st) : launch_fwd<float, FP, 0>(p, st));
+    ACM_DISPATCH_FP(fp, return launch_fwd_mode<float, FP>(p, mode, st));
   }
   return 0;
 }

@@ -79,6 +79,24 @@ int acm_csr_transpose_values(const int64_t* rowptr, const int32_t* col, const fl
 int acm_cast_pad(const float* src, int64_t rows, int64_t cols, int64_t ld_src,
                  void* dst, int dst_dtype, int64_t ld_dst, void* stream);
 
+/* ---- parameter staging ---------------------------------------------------------------------
+ * One launch builds everything the kernels consume from the reference's parameter tensors
+ * (layers.py:41-67): wcat [fin,3fp] T = [W_low|W_high|W_mlp] zero padded, wcat_t [3fp,ldt] T its
+ * transpose (may be NULL), pack (layout above).  a_vecs / ln_gamma / ln_beta are HOST arrays of
+ * k_channels device pointers (ln_* may be NULL when LayerNorm is not live). */
+int acm_pack_params(int dtype, int fin, int f, int fp, int k_channels, int ln_live, int ldt,
+                    const float* w_low, const float* w_high, const float* w_mlp,
+                    const float* const* a_vecs, const float* att_vec,
+                    const float* const* ln_gamma, const float* const* ln_beta,
+                    void* wcat, void* wcat_t, float* pack, void* stream);
+/* The inverse for gradients: dwcat [fin,3fp] / dpack -> dW_* [fin,f], da_k [f], d att_vec [K,K],
+ * d gamma_k / d beta_k [f] (HOST arrays of device pointers; entries may be NULL to skip). */
+int acm_unpack_grads(int fin, int f, int fp, int k_channels, int ln_live,
+                     const float* dwcat, const float* dpack,
+                     float* dw_low, float* dw_high, float* dw_mlp,
+                     float* const* da, float* datt_vec, float* const* dgamma, float* const* dbeta,
+                     void* stream);
+
 /* ---- dense feature transforms -------------------------------------------------------
  * X [n, fin] (row stride ldx), Wcat = [W_low | W_high | W_mlp] zero-padded to
  * [fin(ldw rows used: fin), 3*fp]; WcatT its transpose [3*fp, ldx]. */
