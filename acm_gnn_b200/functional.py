@@ -137,6 +137,38 @@ def _long_pass(csr, transposed, table, fp, halves, cdt, st):
     return rows.data_ptr(), int(rows.numel()), acc.data_ptr(), (rows, acc)
 
 
+def _ptr_array(tensors):
+    """HOST array of device pointers (NULL for None) for the `const float* const*` ABI arguments."""
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def pack_params(cfg, fp, f, fin, ldt, ws, a_vecs, att_vec, ln_params, need_wt, st):
+    """wcat [fin,3fp] T, wcat_t [3fp,ldt] T (or None) and the attention pack in ONE launch."""
+    tdt, cdt = cfg.storage()
+    dev = att_vec.device
+    ws = [w.detach().contiguous() for w in ws]
+    a_vecs = [a.detach().contiguous() for a in a_vecs]
+    av = att_vec.detach().contiguous()
+    wcat = torch.empty(fin, 3 * fp, dtype=tdt, device=dev)
+    wcat_t = torch.empty(3 * fp, ldt, dtype=tdt, device=dev) if need_wt else None
+    pack = torch.empty(12 * fp + 16, dtype=torch.float32, device=dev)
+    k = len(a_vecs)
+    a_arr = _ptr_array(a_vecs)
+    g_arr = b_arr = None
+    keep = [ws, a_vecs, av]
+    if ln_params is not None:
+        gs = [g.detach().contiguous() for g, _ in ln_params]
+        bs = [b.detach().contiguous() for _, b in ln_params]
+        g_arr, b_arr = _ptr_array(gs), _ptr_array(bs)
+        keep += [gs, bs]
+    _lib.call("acm_pack_params", cdt, fin, f, fp, k, int(ln_params is not None), ldt,
+              ws[0].data_ptr(), ws[1].data_ptr(), ws[2].data_ptr(), ctypes.addressof(a_arr), av.data_ptr(),
+              0 if g_arr is None else ctypes.addressof(g_arr), 0 if b_arr is None else ctypes.addressof(b_arr),
+              wcat.data_ptr(), _lib.ptr(wcat_t), pack.data_ptr(), st)
+    del keep
+    return wcat, wcat_t, pack
+
+
 class StagedInput:
     """Layer-0 input features already resident in HBM in the layout the kernels consume: the
     storage-dtype copy padded to the power-of-two width (``xs`` [n_local, ldx]) and, under a row
@@ -203,11 +235,17 @@ class AcmLayerFunction(torch.autograd.Function):
         ln_params = None
         if cfg.ln_live:
             ln_params = [(ln_flat[2 * k], ln_flat[2 * k + 1]) for k in range(K)]
-        pack = build_pack(fp, f, a_vecs, att_vec, ln_params)
-        wcat = build_wcat(fp, f, (w_low, w_high, w_mlp), tdt)
-
         impl = cfg.gemm_impl(fin)
         agg_first = use_aggregate_first(cfg, fin, fp, bool(ctx.needs_input_grad[2]))
+        # row stride of the staged input = K extent of the transposed weights
+        if agg_first:
+            ldt = padded_width(fin)
+        elif staged is not None:
+            ldt = staged.xs.shape[1]
+        else:
+            ldt = (fin + 7) // 8 * 8 if cfg.dtype == "bf16" else fin
+        wcat, wcat_t_all, pack = pack_params(cfg, fp, f, fin, ldt, (w_low, w_high, w_mlp), a_vecs, att_vec, ln_params,
+                                             impl == _lib.GEMM_TCGEN05, st)
         h_i = torch.empty(n, fp, dtype=tdt, device=dev)
         z = d = wcat_t = h_lh = None
         if agg_first:
@@ -233,9 +271,12 @@ class AcmLayerFunction(torch.autograd.Function):
             _lib.call("acm_spmm_agg_first", cdt, ldx, n, op.row0, op.low.rowptr.data_ptr(), op.low.col.data_ptr(),
                       op.low.val.data_ptr(), x_all.data_ptr(), z.data_ptr(), d.data_ptr(), lr[0], lr[1], lr[2], st, tag=ldx)
             del x_all, lr
-            wp = torch.zeros(ldx, 3 * fp, dtype=tdt, device=dev)   # rows fin..ldx are zero
-            wp[:fin] = wcat
-            wt = wp.t().contiguous() if impl == _lib.GEMM_TCGEN05 else None  # [3fp, ldx], K-major
+            if ldx == fin:
+                wp = wcat
+            else:
+                wp = torch.zeros(ldx, 3 * fp, dtype=tdt, device=dev)   # rows fin..ldx are zero
+                wp[:fin] = wcat
+            wt = wcat_t_all  # [3fp, ldx], K-major (tcgen05 path) or None
             for k, (a_op, c_ptr, ldc) in enumerate(((z, h_lh.data_ptr(), 2 * fp),
                                                     (d, h_lh[:, fp:].data_ptr(), 2 * fp),
                                                     (xs, h_i.data_ptr(), fp))):
@@ -268,9 +309,7 @@ class AcmLayerFunction(torch.autograd.Function):
             else:
                 xs = x.detach().contiguous()
                 ldx = fin
-            if impl == _lib.GEMM_TCGEN05:
-                wcat_t = torch.zeros(3 * fp, ldx, dtype=tdt, device=dev)
-                wcat_t[:, :fin] = wcat.t()
+            wcat_t = wcat_t_all
             push = cfg.dist is not None and impl == _lib.GEMM_TCGEN05 and cfg.dist.push_enabled()
             if push:
                 # fused GEMM + all-gather: the epilogue stores every finished [HL|HH] row into all
@@ -420,17 +459,26 @@ class AcmLayerFunction(torch.autograd.Function):
         if cfg.dist is not None:
             cfg.dist.all_reduce_(dwcat)
             cfg.dist.all_reduce_(dpack)
-        if K == 4:
-            d_a_struc = dpack[3 * fp:3 * fp + f].reshape(f, 1).clone()
 
-        dw = [dwcat[:, k * fp:k * fp + f].contiguous() for k in range(3)]
-        da = [dpack[k * fp:k * fp + f].reshape(f, 1).clone() for k in range(3)]
-        d_att_vec = dpack[4 * fp:4 * fp + 16].view(4, 4)[:K, :K].clone()
+        # one launch splits dwcat / dpack into the reference's parameter shapes
+        dw = [torch.empty(fin, f, dtype=torch.float32, device=dev) for _ in range(3)]
+        da = [torch.empty(f, 1, dtype=torch.float32, device=dev) for _ in range(K)]
+        d_att_vec = torch.empty(K, K, dtype=torch.float32, device=dev)
+        n_ln_ch = ctx.n_ln // 2 if cfg.ln_live else 0
+        dg = [torch.empty(f, dtype=torch.float32, device=dev) for _ in range(n_ln_ch)]
+        db = [torch.empty(f, dtype=torch.float32, device=dev) for _ in range(n_ln_ch)]
+        da_arr = _ptr_array(da)
+        dg_arr = _ptr_array(dg + [None] * (K - n_ln_ch)) if n_ln_ch else None
+        db_arr = _ptr_array(db + [None] * (K - n_ln_ch)) if n_ln_ch else None
+        _lib.call("acm_unpack_grads", fin, f, fp, K, int(n_ln_ch > 0), dwcat.data_ptr(), dpack.data_ptr(),
+                  dw[0].data_ptr(), dw[1].data_ptr(), dw[2].data_ptr(), ctypes.addressof(da_arr), d_att_vec.data_ptr(),
+                  0 if dg_arr is None else ctypes.addressof(dg_arr), 0 if db_arr is None else ctypes.addressof(db_arr), st)
+        if K == 4:
+            d_a_struc = da[3]
         d_ln = []
         for k in range(ctx.n_ln // 2):
-            if cfg.ln_live and k < K:
-                d_ln.append(dpack[4 * fp + 16 + k * fp:4 * fp + 16 + k * fp + f].clone())
-                d_ln.append(dpack[8 * fp + 16 + k * fp:8 * fp + 16 + k * fp + f].clone())
+            if k < n_ln_ch:
+                d_ln += [dg[k], db[k]]
             else:
                 d_ln += [None, None]
         return (None, None, dx, dw[0], dw[1], dw[2], da[0], da[1], da[2], d_att_vec, d_struc, d_a_struc, *d_ln)
