@@ -141,6 +141,12 @@ __host__ __device__ __forceinline__ int pack_off_a(int fp, int k) { return k * f
 __host__ __device__ __forceinline__ int pack_off_avec(int fp) { return 4 * fp; }
 __host__ __device__ __forceinline__ int pack_off_gamma(int fp, int k) { return 4 * fp + 16 + k * fp; }
 __host__ __device__ __forceinline__ int pack_off_beta(int fp, int k) { return 8 * fp + 16 + k * fp; }
+// derived tail of the VALUE pack (written by acm_pack_params when LayerNorm is live; not part of
+// the gradient pack): gamma*a per feature and the per-channel sums the row kernels need, so that
+// no CTA has to recompute them (1.25 M CTAs did, ~10 % of the fused forward in LayerNorm mode)
+__host__ __device__ __forceinline__ int pack_off_ga(int fp, int k) { return 12 * fp + 16 + k * fp; }
+__host__ __device__ __forceinline__ int pack_off_sum_ba(int fp) { return 16 * fp + 16; }      // [4] sum_f beta*a
+__host__ __device__ __forceinline__ int pack_off_sum_ga(int fp) { return 16 * fp + 16 + 4; }  // [4] sum_f gamma*a
 
 constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default, ACM-Geometric/layers.py:21-22
 

@@ -103,14 +103,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
   }
   __syncthreads();
   if (LN) {
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (w < KMAX) {
-      float sg = 0.f;
-      for (int i = l; i < FP; i += 32) sg += s_gam[w * FP + i] * s_a[w * FP + i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sg += __shfl_xor_sync(0xffffffffu, sg, o);
-      if (l == 0) s_sum[w] = sg;
-    }
+    if (threadIdx.x < 4) s_sum[threadIdx.x] = p.pack[pack_off_sum_ga(FP) + threadIdx.x];  // precomputed (acm_pack_params)
     __syncthreads();
   }
 

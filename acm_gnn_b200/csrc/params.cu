@@ -32,7 +32,27 @@ __global__ void pack_params_kernel(const PackArgs p) {
   const int w3 = 3 * p.fp;
   const int64_t n_w = (int64_t)p.fin * w3;
   const int64_t n_wt = p.wcat_t ? (int64_t)w3 * p.ldt : 0;
-  const int64_t n_pack = 12 * p.fp + 16;
+  const int64_t n_pack = 16 * p.fp + 32;
+  if (p.ln && blockIdx.x == 0) {
+    // per-channel sums of the derived tail (tiny: one warp per channel)
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (w < p.k) {
+      float sb = 0.f, sg = 0.f;
+      for (int j = l; j < p.f; j += 32) {
+        sb += p.beta[w][j] * p.a[w][j];
+        sg += p.gamma[w][j] * p.a[w][j];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      }
+      if (l == 0) {
+        p.pack[pack_off_sum_ba(p.fp) + w] = sb;
+        p.pack[pack_off_sum_ga(p.fp) + w] = sg;
+      }
+    }
+  }
   if (i < n_w) {
     const int r = (int)(i / w3), c = (int)(i % w3);
     const int k = c / p.fp, j = c % p.fp;
@@ -51,12 +71,16 @@ __global__ void pack_params_kernel(const PackArgs p) {
     } else if (q < 4 * p.fp + 16) {
       const int jj = (q - 4 * p.fp) / 4, kk = (q - 4 * p.fp) % 4;
       if (jj < p.k && kk < p.k) v = p.att_vec[jj * p.k + kk];
+    } else if (q >= 16 * p.fp + 16) {
+      // sums: written above by block 0 (LayerNorm) -- zero the unused slots only
+      const int e = q - (16 * p.fp + 16);
+      if (p.ln && e < 8 && (e & 3) < p.k) return;
     } else if (p.ln) {
       const int q2 = q - 4 * p.fp - 16;
-      const bool is_beta = q2 >= 4 * p.fp;
-      const int q3 = is_beta ? q2 - 4 * p.fp : q2;
+      const int sec = q2 / (4 * p.fp);            // 0 gamma, 1 beta, 2 gamma*a
+      const int q3 = q2 - sec * 4 * p.fp;
       const int k = q3 / p.fp, j = q3 % p.fp;
-      if (k < p.k && j < p.f) v = is_beta ? p.beta[k][j] : p.gamma[k][j];
+      if (k < p.k && j < p.f) v = sec == 0 ? p.gamma[k][j] : (sec == 1 ? p.beta[k][j] : p.gamma[k][j] * p.a[k][j]);
     }
     p.pack[q] = v;
   }
@@ -120,7 +144,7 @@ extern "C" int acm_pack_params(int dtype, int fin, int f, int fp, int k_channels
   }
   p.att_vec = att_vec; p.fin = fin; p.f = f; p.fp = fp; p.k = k_channels; p.ln = ln_live; p.ldt = ldt;
   p.t_bf16 = (dtype == ACM_BF16); p.wcat = wcat; p.wcat_t = wcat_t; p.pack = pack;
-  const int64_t total = (int64_t)fin * 3 * fp + (wcat_t ? (int64_t)3 * fp * ldt : 0) + 12 * fp + 16;
+  const int64_t total = (int64_t)fin * 3 * fp + (wcat_t ? (int64_t)3 * fp * ldt : 0) + 16 * fp + 32;
   pack_params_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   ACM_LAUNCH_CHECK("pack_params");
   return 0;

@@ -340,16 +340,9 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
   for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) s_a[i] = p.pack[i];
   if (threadIdx.x < 16) s_avec[threadIdx.x] = p.pack[pack_off_avec(FP) + threadIdx.x];
   if (LN) {
-    for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x)
-      s_ga[i] = p.pack[pack_off_gamma(FP, 0) + i] * p.pack[i];
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (w < KMAX) {
-      float sb = 0.f;
-      for (int i = l; i < FP; i += 32) sb += p.pack[pack_off_beta(FP, w) + i] * p.pack[pack_off_a(FP, w) + i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
-      if (l == 0) s_sc[w] = sb;
-    }
+    // gamma*a and sum(beta*a) come precomputed in the derived tail of the pack (acm_pack_params)
+    for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) s_ga[i] = p.pack[pack_off_ga(FP, 0) + i];
+    if (threadIdx.x < 4) s_sc[threadIdx.x] = p.pack[pack_off_sum_ba(FP) + threadIdx.x];
   }
   __syncthreads();
 

@@ -102,15 +102,19 @@ def default_dtype() -> str:
 def build_pack(fp, f, a_vecs, att_vec, ln_params):
     """Pack the channel-attention parameters in the layout of include/acm_b200.h."""
     dev = att_vec.device
-    pack = torch.zeros(12 * fp + 16, dtype=torch.float32, device=dev)
+    pack = torch.zeros(16 * fp + 32, dtype=torch.float32, device=dev)
     for k, a in enumerate(a_vecs):
         pack[k * fp:k * fp + f] = a.reshape(-1)
     kk = att_vec.shape[0]
     pack[4 * fp:4 * fp + 16].view(4, 4)[:kk, :kk] = att_vec
     if ln_params is not None:
         for k, (g, b) in enumerate(ln_params):
+            a = a_vecs[k].reshape(-1)
             pack[4 * fp + 16 + k * fp:4 * fp + 16 + k * fp + f] = g
             pack[8 * fp + 16 + k * fp:8 * fp + 16 + k * fp + f] = b
+            pack[12 * fp + 16 + k * fp:12 * fp + 16 + k * fp + f] = g * a       # derived tail
+            pack[16 * fp + 16 + k] = (b * a).sum()
+            pack[16 * fp + 20 + k] = (g * a).sum()
     return pack
 
 
@@ -151,7 +155,7 @@ def pack_params(cfg, fp, f, fin, ldt, ws, a_vecs, att_vec, ln_params, need_wt, s
     av = att_vec.detach().contiguous()
     wcat = torch.empty(fin, 3 * fp, dtype=tdt, device=dev)
     wcat_t = torch.empty(3 * fp, ldt, dtype=tdt, device=dev) if need_wt else None
-    pack = torch.empty(12 * fp + 16, dtype=torch.float32, device=dev)
+    pack = torch.empty(16 * fp + 32, dtype=torch.float32, device=dev)  # ACM_PACK_FLOATS_VALUE
     k = len(a_vecs)
     a_arr = _ptr_array(a_vecs)
     g_arr = b_arr = None

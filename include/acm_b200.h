@@ -44,8 +44,12 @@ extern "C" {
  *   [4*fp       , 4*fp+16)   att_vec[j][k]  row-major 4x4 slots, KxK used        (layers.py:64-67)
  *   [4*fp+16    , 8*fp+16)   ln_gamma[k][fp]  layer_norm_*.weight                (layers.py:52-59)
  *   [8*fp+16    , 12*fp+16)  ln_beta[k][fp]   layer_norm_*.bias
+ * VALUE pack only (derived tail, written by acm_pack_params when LayerNorm is live):
+ *   [12*fp+16   , 16*fp+16)  gamma*a [k][fp]
+ *   [16*fp+16   , 16*fp+24)  sum_f beta*a [4], sum_f gamma*a [4]   (+8 spare)
  */
-#define ACM_PACK_FLOATS(fp) (12 * (fp) + 16)
+#define ACM_PACK_FLOATS(fp) (12 * (fp) + 16)        /* gradient pack */
+#define ACM_PACK_FLOATS_VALUE(fp) (16 * (fp) + 32)  /* value pack incl. derived tail */
 
 int acm_version(void);
 const char* acm_last_error_string(void);

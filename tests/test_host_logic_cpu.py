@@ -25,13 +25,17 @@ def test_pack_layout_matches_header():
     av = torch.arange(16, dtype=torch.float32).reshape(4, 4)
     ln = [(torch.full((f,), 2.0 + k), torch.full((f,), -1.0 - k)) for k in range(4)]
     p = Fn.build_pack(fp, f, a, av, ln)
-    assert p.numel() == 12 * fp + 16
+    assert p.numel() == 16 * fp + 32  # ACM_PACK_FLOATS_VALUE: 12fp+16 parameters + derived LayerNorm tail
     for k in range(4):
         assert torch.equal(p[k * fp:k * fp + f], a[k].reshape(-1))
         assert float(p[k * fp + f:(k + 1) * fp].abs().sum()) == 0.0  # zero padding
         assert torch.equal(p[4 * fp + 16 + k * fp:4 * fp + 16 + k * fp + f], ln[k][0])
         assert torch.equal(p[8 * fp + 16 + k * fp:8 * fp + 16 + k * fp + f], ln[k][1])
     assert torch.equal(p[4 * fp:4 * fp + 16].view(4, 4), av)
+    for k in range(4):  # derived tail: gamma*a and the per-channel sums
+        assert torch.allclose(p[12 * fp + 16 + k * fp:12 * fp + 16 + k * fp + f], ln[k][0] * a[k].reshape(-1))
+        assert float(p[16 * fp + 16 + k]) == pytest.approx(float((ln[k][1] * a[k].reshape(-1)).sum()))
+        assert float(p[16 * fp + 20 + k]) == pytest.approx(float((ln[k][0] * a[k].reshape(-1)).sum()))
     # 3x3 att_vec lands in the top-left of the 4x4 slot block
     p3 = Fn.build_pack(fp, f, a[:3], av[:3, :3].contiguous(), None)
     assert torch.equal(p3[4 * fp:4 * fp + 16].view(4, 4)[:3, :3], av[:3, :3])
