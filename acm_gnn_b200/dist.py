@@ -83,7 +83,9 @@ class RowPartition:
         Alternating buffers removes the "everybody is done reading" barrier before a push: a
         buffer is rewritten two uses later, and by then every rank has passed the post-push
         barrier of the use in between, which it can only reach after finishing its reads of this
-        buffer (stream order)."""
+        buffer (stream order).  Consequence: at most TWO forwards of the same layer may be
+        outstanding before their backwards run (variant 1 keeps a view of the forward table for
+        its relu mask); deeper gradient accumulation needs ACMB200_PUSH=0."""
         par = self._symm.get(("parity", key), 0)
         self._symm[("parity", key)] = par ^ 1
         k = (key, par, width, dtype)

@@ -8,6 +8,9 @@ Math (validated against the reference, SURVEY.md section 8a / DESIGN.md):
        O_I = relu(HI) ; [O_S = relu(A_raw S)] ; att = softmax(sigmoid([LN](O_k).a_k) Avec / K)
        Y = c * sum_k att_k O_k       (c = 3, or 1 with the structure channel; layers.py:200-232)
   bwd  mix_bwd (row local) -> transposed aggregation -> dWcat = X^T dH, dX = dH Wcat^T
+Aggregate-first order (variant 0, input without gradient, pad(Fin) <= 2*FP; default):
+  fwd  Z = A X ; D = X - Z ; [S_L|S_H|HI] = [Z W_L | D W_H | X W_I] ; epilogue as above
+  bwd  dW_L = Z^T dS_L ; dW_H = D^T dS_H ; dW_I = X^T dHI          (no transposed aggregation)
 """
 from __future__ import annotations
 
