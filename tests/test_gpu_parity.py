@@ -481,3 +481,33 @@ def test_bf16_interlayer_activations_equivalent(monkeypatch):
     assert torch.equal(res["1"][0], res["0"][0])
     _close_grad(res["1"][1], res["0"][1], "bf16", "dW0")
     _close_grad(res["1"][2], res["0"][2], "bf16", "dW1")
+
+
+@pytest.mark.parametrize("variant", [False, True])
+def test_training_with_dropout_runs_and_is_finite(variant):
+    """dropout > 0 in training mode (the reference sweeps use up to 0.7): a fresh tensor reaches
+    layer 1 every step (bf16 activations + random mask), gradients stay finite, the loss of a few
+    Adam steps decreases."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200.functional import nll_log_softmax
+    os.environ["ACMB200_DTYPE"] = "bf16"
+    g = Golden("gcn_pt_acmgcn_v0")
+    torch.manual_seed(0)
+    model = A.GCN(g.nfeat, 64, g.nclass, 2, g.n, 0.5, "acmgcn", 0, variant=variant).cuda()
+    op = A.AcmOperator.from_edges(torch.from_numpy(g.row).cuda(), torch.from_numpy(g.col).cuda(), g.n)
+    x, labels = g.x.cuda(), g.labels.cuda()
+    mask = torch.zeros(g.n, dtype=torch.uint8, device="cuda")
+    mask[g.idx_train.cuda()] = 1
+    opt = torch.optim.Adam([p for k, p in model.named_parameters() if k not in ("fea_param", "xX_param")], lr=0.05)
+    losses = []
+    model.train()
+    for _ in range(25):
+        opt.zero_grad(set_to_none=True)
+        loss = nll_log_softmax(model(x, op, None, None), labels, mask)
+        loss.backward()
+        for k, p in model.named_parameters():
+            if p.grad is not None:
+                assert torch.isfinite(p.grad).all(), k
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0]
