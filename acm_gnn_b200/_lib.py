@@ -78,7 +78,7 @@ def load():
             fn.restype = _RESTYPES.get(name, _c.c_int)
         g = os.environ.get("ACMB200_GATHER")
         if g is not None:
-            lib.acm_set_gather_mode(1 if g.lower() in ("1", "async", "cp.async") else 0)
+            lib.acm_set_gather_mode({"1": 1, "async": 1, "cp.async": 1, "2": 2, "bulk": 2}.get(g.lower(), 0))
         r = os.environ.get("ACMB200_MIXBWD_RING")
         if r is not None:
             lib.acm_set_mix_bwd_ring(int(r))

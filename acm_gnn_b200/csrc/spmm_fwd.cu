@@ -57,7 +57,34 @@ template <typename T> __device__ __forceinline__ void cp_async_slice(uint32_t ds
   if (sizeof(T) == 4) cp_async16(dst + 16, reinterpret_cast<const char*>(src) + 16);
 }
 
-template <typename T, int FP, int MODE, bool ASYNC>
+// ---- bulk-copy gather (gather mode 2, FP = 256 only: one row per warp) -------------------------
+// The neighbour's whole [HL|HH] table row (1 KB in bf16) is one contiguous span, so ONE
+// cp.async.bulk (the TMA engine's linear-copy form, SASS UBLKCP) issued by lane 0 replaces the
+// 64 per-lane LDGSTS of mode 1; completion is tracked per ring slot by an mbarrier
+// (arrive.expect_tx by the issuing lane, complete_tx by the copy engine).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// GM: 0 register-staged LDG gather, 1 cp.async (LDGSTS) ring, 2 cp.async.bulk ring (FP = 256)
+template <typename T, int FP, int MODE, int GM>
 __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t rb, const float* s_a,
                                               const float* s_avec, const float* s_ga, const float* s_sc,
                                               uint8_t* s_ring) {
@@ -99,7 +126,56 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
     e = e1;
   }
 
-  if (ASYNC && e < e1) {
+  if (GM == 2 && LANES == 32 && e < e1) {
+    constexpr int ST = AsyncCfg<T>::kStages;
+    constexpr uint32_t ROWB = TW * (uint32_t)sizeof(T);   // one table row = one ring slot
+    constexpr int SB = 8 * (int)sizeof(T);
+    uint8_t* ring = s_ring + warp * (ST * ROWB);
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+    // the mbarriers follow the kFwdWarps rings
+    const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(s_ring + kFwdWarps * (ST * ROWB)) + warp * (ST * 8);
+    const T* __restrict__ tab0 = reinterpret_cast<const T*>(p.table);
+    const int n_e = (int)(e1 - e);
+    // column indices / weights travel in registers, 32 edges per coalesced load, broadcast by shuffle
+    int32_t ccur = (lane < n_e) ? __ldg(col + e + lane) : 0;
+    float wcur = (val && lane < n_e) ? __ldg(val + e + lane) : 1.f;
+#pragma unroll
+    for (int st = 0; st < ST; ++st) {
+      const int32_t c = __shfl_sync(0xffffffffu, ccur, st);
+      if (lane == 0 && st < n_e) {
+        mbar_expect_tx(bar_u32 + st * 8, ROWB);
+        bulk_copy_g2s(ring_u32 + st * ROWB, tab0 + (int64_t)c * TW, ROWB, bar_u32 + st * 8);
+      }
+    }
+    for (int i = 0; i < n_e; ++i) {
+      const int slot = i & (ST - 1);
+      if ((i & 31) == 0 && i) wcur = (val && i + lane < n_e) ? __ldg(val + e + i + lane) : 1.f;
+      const int j = i + ST;                            // edge whose copy re-fills this slot
+      if ((j & 31) == 0) ccur = (j + lane < n_e) ? __ldg(col + e + j + lane) : 0;
+      const float w = __shfl_sync(0xffffffffu, wcur, i & 31);
+      const int32_t cn = __shfl_sync(0xffffffffu, ccur, j & 31);
+      mbar_wait(bar_u32 + slot * 8, (i / ST) & 1);
+      Slice8<T> vl, vh;
+      vl.load_plain(reinterpret_cast<const T*>(ring + slot * ROWB + lane * SB));
+      vh.load_plain(reinterpret_cast<const T*>(ring + slot * ROWB + FP * sizeof(T) + lane * SB));
+      float fl[8], fh[8];
+      vl.to_float(fl);
+      vh.to_float(fh);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        accL[t] = fmaf(w, fl[t], accL[t]);
+        accH[t] = fmaf(w, fh[t], accH[t]);
+      }
+      __syncwarp();                                    // every lane has read the slot
+      if (lane == 0 && j < n_e) {
+        mbar_expect_tx(bar_u32 + slot * 8, ROWB);
+        bulk_copy_g2s(ring_u32 + slot * ROWB, tab0 + (int64_t)cn * TW, ROWB, bar_u32 + slot * 8);
+      }
+    }
+    e = e1;
+  }
+
+  if (GM == 1 && e < e1) {
     constexpr int ST = AsyncCfg<T>::kStages;
     constexpr int SB = 8 * (int)sizeof(T);           // bytes of one 8-feature slice
     constexpr int STAGE_BYTES = 64 * SB;             // per warp: 32 L slices then 32 H slices
@@ -326,7 +402,7 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
   }
 }
 
-template <typename T, int FP, int MODE, bool ASYNC>
+template <typename T, int FP, int MODE, int GM>
 __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdParams p) {
   constexpr bool LN = (MODE & 1) != 0;
   constexpr int KMAX = (MODE & 2) ? 4 : 3;
@@ -352,17 +428,35 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
     // parameter-pack load above -> grid-stride over row blocks
     const int64_t n_blocks = (p.n_rows + (int64_t)kFwdWarps * RPWk - 1) / ((int64_t)kFwdWarps * RPWk);
     for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x)
-      fwd_row_block<T, FP, MODE, false>(p, rb, s_a, s_avec, s_ga, s_sc, nullptr);
+      fwd_row_block<T, FP, MODE, 0>(p, rb, s_a, s_avec, s_ga, s_sc, nullptr);
   } else {
     // gather mode: one row block per CTA; the hardware block scheduler balances the degrees
     // the cp.async ring follows the parameter pack in dynamic shared memory (16-byte aligned)
     constexpr int kPackFloats = KMAX * FP + 16 + (LN ? KMAX * FP + 8 : 0);
     uint8_t* s_ring = reinterpret_cast<uint8_t*>(smem + ((kPackFloats + 3) & ~3));
-    fwd_row_block<T, FP, MODE, ASYNC>(p, blockIdx.x, s_a, s_avec, s_ga, s_sc, s_ring);
+    if (GM == 2) {
+      // one mbarrier per ring slot per warp; the __syncthreads below publishes the inits
+      constexpr int ST = AsyncCfg<T>::kStages;
+      if (threadIdx.x < kFwdWarps * ST)
+        mbar_init((uint32_t)__cvta_generic_to_shared(s_ring + kFwdWarps * ST * (2 * FP * sizeof(T))) + threadIdx.x * 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      __syncthreads();
+    }
+    fwd_row_block<T, FP, MODE, GM>(p, blockIdx.x, s_a, s_avec, s_ga, s_sc, s_ring);
   }
 }
 
-static int g_gather_mode = 1;  // 0: LDG register staging, 1: cp.async shared-memory ring
+static int g_gather_mode = 1;  // 0: LDG register staging, 1: cp.async ring, 2: cp.async.bulk ring (FP = 256)
+
+template <typename K>
+static int raise_smem(K kernel, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    set_error("spmm_mix_fwd: cannot raise dynamic shared memory to %zu: %s", smem, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
 
 template <typename T, int FP, int MODE>
 static int launch_fwd(const FwdParams& p, cudaStream_t st) {
@@ -377,23 +471,21 @@ static int launch_fwd(const FwdParams& p, cudaStream_t st) {
   // the ring pays off for wide rows (FP = 256: 97 % vs 91 % of HBM peak); for narrow rows (FP = 16,
   // two lanes per row) the per-edge commit/wait overhead costs more than it hides (measured 5.4 vs
   // 4.8 ms), so they keep the register-staged LDG loop
-  const bool async = g_gather_mode == 1 && !p.pre_agg && FP >= 64;
+  const int gm = p.pre_agg ? 0
+                 : (g_gather_mode == 2 && FP == 256) ? 2
+                 : (g_gather_mode >= 1 && FP >= 64) ? 1 : 0;
   size_t smem = sizeof(float) * ((kPackFloats + 3) & ~3);
-  if (async) {
+  if (gm == 2) {
+    constexpr int GMB = FP == 256 ? 2 : 1;   // the bulk ring is only instantiated for FP = 256
+    smem += (size_t)kFwdWarps * AsyncCfg<T>::kStages * (2 * FP * sizeof(T) + 8);
+    if (int rc = raise_smem(spmm_mix_fwd_kernel<T, FP, MODE, GMB>, smem)) return rc;
+    spmm_mix_fwd_kernel<T, FP, MODE, GMB><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
+  } else if (gm == 1) {
     smem += (size_t)kFwdWarps * AsyncCfg<T>::kStages * 64 * 8 * sizeof(T);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(spmm_mix_fwd_kernel<T, FP, MODE, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) {
-        set_error("spmm_mix_fwd: cannot raise dynamic shared memory to %zu: %s", smem, cudaGetErrorString(e));
-        return (int)e;
-      }
-      attr_set = true;
-    }
-    spmm_mix_fwd_kernel<T, FP, MODE, true><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
+    if (int rc = raise_smem(spmm_mix_fwd_kernel<T, FP, MODE, 1>, smem)) return rc;
+    spmm_mix_fwd_kernel<T, FP, MODE, 1><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
   } else {
-    spmm_mix_fwd_kernel<T, FP, MODE, false><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
+    spmm_mix_fwd_kernel<T, FP, MODE, 0><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
   }
   ACM_LAUNCH_CHECK("spmm_mix_fwd");
   return 0;
@@ -447,8 +539,8 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
 }
 
 extern "C" int acm_set_gather_mode(int mode) {
-  if (mode != 0 && mode != 1) {
-    acm::set_error("gather mode must be 0 (LDG) or 1 (cp.async ring)");
+  if (mode < 0 || mode > 2) {
+    acm::set_error("gather mode must be 0 (LDG), 1 (cp.async ring) or 2 (cp.async.bulk ring)");
     return ACM_ERR_BAD_ARG;
   }
   acm::g_gather_mode = mode;

@@ -436,7 +436,39 @@ def test_degree_skew_long_rows_squirrel(order, mode, monkeypatch):
         _close_grad(getattr(layer, k).grad, p[k].grad, mode, "d" + k)
 
 
-@pytest.mark.parametrize("gather", ["0", "1"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("gather", [1, 2])
+def test_gather_modes_agree_wide_rows(gather, mode):
+    """Width 256 (one row per warp) is where gather mode 2 (cp.async.bulk ring, one 1-KB copy per
+    neighbour row) applies.  Degrees from 1 to > 100 exercise the ring wrap-around (8 / 4 slots)
+    and the 32-edge register chunks of column indices and weights.  Same accumulation order in
+    every mode -> bitwise equal outputs."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    os.environ["ACMB200_DTYPE"] = mode
+    os.environ["ACMB200_REORDER"] = "off"
+    try:
+        n = 1500
+        row, col = O.synthetic_edges(n, 60000, seed=5)
+        op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+        deg = (op.low.rowptr[1:] - op.low.rowptr[:-1])
+        assert int(deg.max()) > 40 and int(deg.min()) >= 1
+        torch.manual_seed(3)
+        layer = A.GraphConvolution(48, 256, n, "acmgcn", variant=False).cuda()
+        x = torch.rand(n, 48, device="cuda")
+        outs = []
+        for gm in (0, gather):
+            _lib.call("acm_set_gather_mode", gm)
+            outs.append(layer(x, op, None, None).detach().clone())
+        torch.cuda.synchronize()
+        assert torch.isfinite(outs[0]).all()
+        assert torch.equal(outs[0], outs[1])
+    finally:
+        _lib.call("acm_set_gather_mode", 1)
+        os.environ.pop("ACMB200_REORDER", None)
+
+
+@pytest.mark.parametrize("gather", ["0", "1", "2"])
 def test_gather_modes_agree(gather):
     """acm_set_gather_mode: the cp.async shared-memory ring and the LDG register-staged gather
     produce the same sums (fp32 storage: identical accumulation order -> bitwise equal)."""
