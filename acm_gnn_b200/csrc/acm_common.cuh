@@ -129,12 +129,33 @@ __device__ __forceinline__ int find_long_row(const LongRows& lr, int64_t row) {
 // tables through NVLink peer mappings (symmetric memory): the transfer overlaps the compute and
 // the all-gather disappears as a separate step.  tables[r] = base of rank r's [N_pad, width]
 // table; rows are written at global index row_off + local row.
+//
+// NVSwitch multicast (NVLS): when the symmetric allocation also has a multicast mapping, `mc` is
+// the multicast address of the same table and ONE multimem.st per 16 bytes replaces the n peer
+// stores -- the switch replicates the write into every rank's copy (the own one included), so a
+// rank's NVLink egress drops from (n-1) x to 1 x the bytes it produced.
 constexpr int kMaxPeers = 8;
 struct PeerTables {
   void* tables[kMaxPeers];
+  void* mc;            // multicast address of the table, or nullptr -> unicast peer stores
   int n;               // 0 = no push (single GPU / NCCL path)
   int64_t row_off;
 };
+
+__device__ __forceinline__ void multimem_st16(void* addr, const uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(__uint_as_float(v.x)),
+               "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+               : "memory");
+}
+// 16 bytes to byte offset `off` of every rank's table
+__device__ __forceinline__ void peer_store16(const PeerTables& pt, const int64_t off, const uint4 v) {
+  if (pt.mc) {
+    multimem_st16(reinterpret_cast<char*>(pt.mc) + off, v);
+  } else {
+#pragma unroll 1
+    for (int r = 0; r < pt.n; ++r) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(pt.tables[r]) + off) = v;
+  }
+}
 
 // layout of the attention parameter pack (see acm_b200.h)
 __host__ __device__ __forceinline__ int pack_off_a(int fp, int k) { return k * fp; }

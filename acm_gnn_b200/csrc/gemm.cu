@@ -138,13 +138,13 @@ extern "C" int acm_gemm_bwd_dx(int impl, int dtype, const void* dh, const void* 
 }
 
 extern "C" int acm_gemm_xw_fwd_push(const void* x, int64_t ldx, const void* wcat_t, void* const* peer_tables, int n_peers,
-                                    int64_t row_off, void* h_i, int64_t n, int64_t fin, int64_t fp, int relu_lh,
-                                    void* stream) {
+                                    int64_t row_off, void* multicast_table, void* h_i, int64_t n, int64_t fin,
+                                    int64_t fp, int relu_lh, void* stream) {
   using namespace acm;
   ACM_CHECK_ARG(x && wcat_t && peer_tables && h_i, "gemm_xw_fwd_push: null pointer");
   ACM_CHECK_ARG(n_peers >= 1 && n_peers <= kMaxPeers, "gemm_xw_fwd_push: 1 <= n_peers <= %d", kMaxPeers);
   PeerTables pt{};
-  pt.n = n_peers; pt.row_off = row_off;
+  pt.n = n_peers; pt.row_off = row_off; pt.mc = multicast_table;
   for (int r = 0; r < n_peers; ++r) pt.tables[r] = peer_tables[r];
   return tc_gemm_fwd(x, ldx, wcat_t, nullptr, h_i, n, fin, fp, relu_lh, &pt, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -240,9 +240,7 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               if (p.peers.n > 0) {
                 // fused all-gather: the finished row segment goes to every rank's table over NVLink
                 const int64_t off = (p.peers.row_off + row) * p.ldc0 + j;
-#pragma unroll 1
-                for (int r = 0; r < p.peers.n; ++r)
-                  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.peers.tables[r]) + off) = packed;
+                peer_store16(p.peers, off * (int64_t)sizeof(__nv_bfloat16), packed);
               } else {
                 *reinterpret_cast<uint4*>(p.c0 + row * p.ldc0 + j) = packed;
               }

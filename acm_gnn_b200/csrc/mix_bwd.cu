@@ -329,11 +329,15 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
       if (rows_valid > 0) {
         const int n_vec = (int)(rows_valid * TW * sizeof(T) / 16);
         const uint4* src = reinterpret_cast<const uint4*>(stg);
-        const int64_t off = (p.peers.row_off + first_row) * TW;
+        const int64_t off = (p.peers.row_off + first_row) * TW * (int64_t)sizeof(T);
+        if (p.peers.mc) {
+          for (int v = lane; v < n_vec; v += 32) multimem_st16(reinterpret_cast<char*>(p.peers.mc) + off + v * 16, src[v]);
+        } else {
 #pragma unroll 1
-        for (int r = 0; r < p.peers.n; ++r) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.peers.tables[r]) + off);
-          for (int v = lane; v < n_vec; v += 32) dst[v] = src[v];
+          for (int r = 0; r < p.peers.n; ++r) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(p.peers.tables[r]) + off);
+            for (int v = lane; v < n_vec; v += 32) dst[v] = src[v];
+          }
         }
       }
       __syncwarp();
@@ -349,8 +353,17 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
             // fused all-gather of the backward operand table (see PeerTables): wide rows, every
             // warp store already covers 512 contiguous bytes
             const int64_t off = (p.peers.row_off + row) * TW + f0 + k * FP;
+            if (p.peers.mc) {
+              // stage the slice in registers in storage format, then one (bf16) / two (fp32) multicast stores
+              uint4 pk[sizeof(T) == 2 ? 1 : 2];
+              Slice8<T>::store(reinterpret_cast<T*>(pk), out);
+#pragma unroll
+              for (int h = 0; h < (int)(sizeof(pk) / 16); ++h)
+                multimem_st16(reinterpret_cast<char*>(p.peers.mc) + off * (int64_t)sizeof(T) + h * 16, pk[h]);
+            } else {
 #pragma unroll 1
-            for (int r = 0; r < p.peers.n; ++r) Slice8<T>::store(reinterpret_cast<T*>(p.peers.tables[r]) + off, out);
+              for (int r = 0; r < p.peers.n; ++r) Slice8<T>::store(reinterpret_cast<T*>(p.peers.tables[r]) + off, out);
+            }
           } else {
             Slice8<T>::store(reinterpret_cast<T*>(p.t_lh) + row * TW + f0 + k * FP, out);
           }
@@ -446,7 +459,8 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
                            const float* att, const float* sig, const float* pack,
                            int k_channels, int ln_live, int variant, float out_scale,
                            void* t_lh, void* dh_all, void* dos_pre, float* dpack,
-                           void* const* peer_tables, int n_peers, int64_t peer_row_off, void* stream) {
+                           void* const* peer_tables, int n_peers, int64_t peer_row_off, void* multicast_table,
+                           void* stream) {
   using namespace acm;
   ACM_CHECK_ARG(n_peers >= 0 && n_peers <= kMaxPeers, "mix_bwd: 0 <= n_peers <= %d", kMaxPeers);
   ACM_CHECK_ARG(n_peers == 0 || peer_tables, "mix_bwd: peer push needs peer_tables");
@@ -462,7 +476,7 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
   p.pack = pack; p.k = k_channels; p.ln = ln_live; p.variant = variant; p.f = f; p.out_scale = out_scale;
   p.t_lh = t_lh; p.dh_all = dh_all; p.dos_pre = dos_pre; p.dpack = dpack;
   p.peers = PeerTables{};
-  p.peers.n = n_peers; p.peers.row_off = peer_row_off;
+  p.peers.n = n_peers; p.peers.row_off = peer_row_off; p.peers.mc = n_peers > 0 ? multicast_table : nullptr;
   for (int r = 0; r < n_peers; ++r) p.peers.tables[r] = peer_tables[r];
   // cp.async ring: needs 16-byte aligned, unpadded rows (f == fp) of every streamed input
   const bool g_ok = p.g_bf16 ? (ldg % 8 == 0) : (ldg % 4 == 0);

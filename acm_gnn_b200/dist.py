@@ -32,6 +32,7 @@ class RowPartition:
         self.bytes_gathered = 0
         self._symm = {}
         self._push_ok = None
+        self.multicast = False   # set by symm_table: exchange pushes go through NVSwitch multicast
 
     def bounds(self, rank):
         r0 = min(self.n_global, rank * self.rows_per_rank)
@@ -78,7 +79,12 @@ class RowPartition:
     def symm_table(self, key, width, dtype, device):
         """Persistent [world*rows_per_rank, width] table in symmetric memory, TWO per (layer,
         direction), used alternately.  Returns (tensor, handle, ctypes array of the ``world``
-        peer base pointers).
+        peer base pointers, multicast address or 0).  The multicast (NVLS) address is non-zero when
+        the driver mapped the allocation into an NVSwitch multicast object: the kernels then issue
+        one ``multimem.st`` per 16 bytes instead of ``world`` peer stores.  Opt-in with
+        ACMB200_MULTICAST=1: measured on 4 B200s it is slightly SLOWER than the unicast stores (an
+        all-gather is bound by every rank's NVLink ingress, and the multicast loop-back of the own
+        rows adds 1/world to it), so unicast stays the default.
 
         Alternating buffers removes the "everybody is done reading" barrier before a push: a
         buffer is rewritten two uses later, and by then every rank has passed the post-push
@@ -96,7 +102,13 @@ class RowPartition:
         t = symm.empty((self.world * self.rows_per_rank, width), dtype=dtype, device=device)
         hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
         ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
-        self._symm[k] = (t, hdl, ptrs)
+        mc = 0
+        if os.environ.get("ACMB200_MULTICAST", "0") == "1":
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            if mc:  # same offset inside the allocation as the tensor has from its unicast base
+                mc += t.data_ptr() - int(hdl.buffer_ptrs[dist.get_rank(self.group)])
+        self.multicast = bool(mc)
+        self._symm[k] = (t, hdl, ptrs, mc)
         return self._symm[k]
 
     def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:

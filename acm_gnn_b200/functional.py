@@ -322,9 +322,9 @@ class AcmLayerFunction(torch.autograd.Function):
                 # fused GEMM + all-gather: the epilogue stores every finished [HL|HH] row into all
                 # ranks' tables through NVLink peer mappings; one device-side barrier afterwards
                 # (tables alternate between two buffers, see RowPartition.symm_table)
-                table, hdl, ptrs = cfg.dist.symm_table((cfg.layer_key, "fwd"), 2 * fp, tdt, dev)
+                table, hdl, ptrs, mc = cfg.dist.symm_table((cfg.layer_key, "fwd"), 2 * fp, tdt, dev)
                 _lib.call("acm_gemm_xw_fwd_push", xs.data_ptr(), ldx, wcat_t.data_ptr(), ctypes.addressof(ptrs),
-                          cfg.dist.world, op.row0, h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
+                          cfg.dist.world, op.row0, mc, h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
                 hdl.barrier(channel=0)     # every rank's rows have landed everywhere
                 h_lh = table[op.row0:op.row0 + n]
             else:
@@ -398,11 +398,11 @@ class AcmLayerFunction(torch.autograd.Function):
         push = (cfg.dist is not None and not ctx.agg_first and cfg.dist.push_enabled())
         if push:
             # fused mix_bwd + all-gather of the backward operand table (peer stores over NVLink)
-            t_table, hdl, ptrs = cfg.dist.symm_table((cfg.layer_key, "bwd"), 2 * fp, tdt, dev)
+            t_table, hdl, ptrs, mc = cfg.dist.symm_table((cfg.layer_key, "bwd"), 2 * fp, tdt, dev)
             _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), gdt, f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
                       att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
                       float(cfg.out_scale), 0, dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
-                      ctypes.addressof(ptrs), cfg.dist.world, op.row0, st, tag=fp)
+                      ctypes.addressof(ptrs), cfg.dist.world, op.row0, mc, st, tag=fp)
             hdl.barrier(channel=0)
             t_lh = None
         else:
@@ -410,7 +410,7 @@ class AcmLayerFunction(torch.autograd.Function):
             _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), gdt, f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
                       att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
                       float(cfg.out_scale), t_lh.data_ptr(), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
-                      0, 0, 0, st, tag=fp)
+                      0, 0, 0, 0, st, tag=fp)
 
         dwcat = torch.zeros(fin, 3 * fp, dtype=torch.float32, device=dev)
         dx = None

@@ -210,7 +210,7 @@ def workload_config(args, world):
                         + (" (SURVEY 8d cfg 5)" if args.nodes == 10_000_000 else ""),
             "skew": args.skew, "nodes": args.nodes, "edges": args.edges, "fin": args.fin, "hidden": args.hidden, "nclass": args.nclass,
             "step": "forward + log_softmax/NLL (" + ("torch glue" if args.torch_loss else "fused acm_nll_log_softmax") + ") + backward + Adam.step",
-            "partition": f"1-D row partition over {world} GPU(s), NCCL all-gather of the operand table" if world > 1 else "single GPU",
+            "partition": f"1-D row partition over {world} GPU(s)" if world > 1 else "single GPU",
             "input_staging": "raw fp32 features every step" if args.no_stage_input else "features staged once in the kernel layout (bf16, padded, all-gathered across ranks) before the timed region; e2e starts from host fp32 buffers every step",
             "l2": "inputs >> L2 (no flush)" if args.nodes * args.hidden * 2 > 4 * 126e6 else "L2 flushed between timed steps"}
 
@@ -514,7 +514,11 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": dict(workload_config(args, world), exchange=(
+                "none (single GPU)" if part is None else
+                "operand tables all-gathered by NCCL" if not part.push_enabled() else
+                "fused into the producing kernels: rows pushed into every rank's table over NVLink "
+                + ("through NVSwitch multicast (multimem.st)" if part.multicast else "peer mappings (unicast stores)"))),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches,
             "nnz": nnz_global, "max_degree": max_deg, "long_rows": n_long_rows, "peak_mem_gb": round(peak_mem, 2), "loss": final_loss,
             "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first in layer 0 (A(XW)=(AX)W, SURVEY 8f rank 4), transform-first fused SpMM+mix in layer 1" if key_agg in summ else "transform-first (north-star fused SpMM+mix) in both layers",

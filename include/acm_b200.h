@@ -116,9 +116,14 @@ int acm_gemm_xw_fwd(int impl, int dtype, const void* x, int64_t ldx, const void*
  * rank's [N_pad, 2*fp] gather table mapped into this process (symmetric memory over NVLink);
  * each finished [HL|HH] row is stored into all of them at row index row_off + local row, so the
  * exchange overlaps the GEMM and no separate collective runs (tcgen05 / bf16 path only).
- * acm_mix_bwd takes the same (peer_tables, n_peers, peer_row_off) triple for the backward table. */
+ * multicast_table: NULL, or the NVSwitch multicast (NVLS) address of the same table -- then one
+ * multimem.st per 16 bytes replaces the n_peers unicast stores and the switch replicates the row
+ * into every rank's copy (egress 1x instead of (n_peers-1)x the produced bytes).
+ * acm_mix_bwd takes the same (peer_tables, n_peers, peer_row_off, multicast_table) for the
+ * backward table. */
 int acm_gemm_xw_fwd_push(const void* x, int64_t ldx, const void* wcat_t, void* const* peer_tables, int n_peers,
-                         int64_t row_off, void* h_i, int64_t n, int64_t fin, int64_t fp, int relu_lh, void* stream);
+                         int64_t row_off, void* multicast_table, void* h_i, int64_t n, int64_t fin, int64_t fp,
+                         int relu_lh, void* stream);
 
 /* autograd of the three torch.mm: dWcat[fin, 3*fp] (fp32, zeroed by caller; accumulated
  * atomically over split-K slices) = X^T . dH,  dH [n, 3*fp] = [dHL | dHH | dHI]. */
@@ -199,7 +204,7 @@ int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
                 const float* att, const float* sig, const float* pack,
                 int k_channels, int ln_live, int variant, float out_scale,
                 void* t_lh, void* dh_all, void* dos_pre, float* dpack,
-                void* const* peer_tables, int n_peers, int64_t peer_row_off, void* stream);
+                void* const* peer_tables, int n_peers, int64_t peer_row_off, void* multicast_table, void* stream);
 
 /* Transposed aggregation (autograd of torch.spmm(adj_low,.) / torch.spmm(adj_high,.)):
  *   dHL = A_low^T dS_L ; dHH = dS_H - A_low^T dS_H     -> dh_all[:, 0:2fp]

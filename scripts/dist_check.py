@@ -23,12 +23,16 @@ def main():
     from acm_gnn_b200.functional import nll_log_softmax
     L.device = dev
     ok_all = True
-    for mode, variant, n, staged, struct in (("fp32", False, 5003, False, 0), ("bf16", False, 5003, False, 0),
-                                             ("fp32", True, 4096, False, 0), ("fp32", False, 5003, True, 0),
-                                             ("bf16", False, 4100, True, 0), ("bf16", True, 4100, False, 0),
-                                             ("fp32", False, 3001, False, 1), ("bf16", True, 3001, False, 1)):
+    # hidden 64: narrow-row (smem-staged) pushes; hidden 256 + variant 1: wide-row pushes in the GEMM
+    # epilogue and in mix_bwd
+    for mode, variant, n, staged, struct, hid in (("fp32", False, 5003, False, 0, 64), ("bf16", False, 5003, False, 0, 64),
+                                                  ("fp32", True, 4096, False, 0, 64), ("fp32", False, 5003, True, 0, 64),
+                                                  ("bf16", False, 4100, True, 0, 64), ("bf16", True, 4100, False, 0, 64),
+                                                  ("fp32", False, 3001, False, 1, 64), ("bf16", True, 3001, False, 1, 64),
+                                                  ("bf16", True, 4100, False, 0, 256), ("fp32", True, 4100, False, 0, 256),
+                                                  ("bf16", False, 4100, True, 0, 256)):
         os.environ["ACMB200_DTYPE"] = mode
-        fin, hid, ncls = 48, 64, 7
+        fin, ncls = 48, 7
         g = torch.Generator(device=dev); g.manual_seed(5)
         src = torch.randint(0, n, (40000,), generator=g, device=dev)
         dst = torch.randint(0, n, (40000,), generator=g, device=dev)
@@ -73,7 +77,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         ok_all = ok_all and bool(t.item())
         if rank == 0:
-            print(f"dist_check world={world} mode={mode} variant={variant} staged={staged} struct={struct} push={part.push_enabled()} n={n}: out rel.err {e_out:.2e}, worst grad rel.fro {worst:.2e} -> {'OK' if t.item() else 'FAIL'}", flush=True)
+            print(f"dist_check world={world} mode={mode} variant={variant} staged={staged} struct={struct} hid={hid} push={part.push_enabled()} multicast={part.multicast} n={n}: out rel.err {e_out:.2e}, worst grad rel.fro {worst:.2e} -> {'OK' if t.item() else 'FAIL'}", flush=True)
     if rank == 0:
         print("DIST_CHECK", "PASS" if ok_all else "FAIL", flush=True)
     dist.destroy_process_group()
