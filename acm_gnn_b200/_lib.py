@@ -40,6 +40,7 @@ _PROTOS = {
     "acm_nll_log_softmax": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _i64, _vp],
     "acm_set_l2_fetch_granularity": [_i32],
     "acm_set_gather_mode": [_i32],
+    "acm_set_narrow_row_hint": [_i32],
     "acm_set_mix_bwd_occupancy": [_i32],
     "acm_set_mix_bwd_ring": [_i32],
     "acm_gemm_ab": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
@@ -79,6 +80,9 @@ def load():
         g = os.environ.get("ACMB200_GATHER")
         if g is not None:
             lib.acm_set_gather_mode({"1": 1, "async": 1, "cp.async": 1, "2": 2, "bulk": 2}.get(g.lower(), 0))
+        h = os.environ.get("ACMB200_NARROW_HINT")
+        if h is not None:
+            lib.acm_set_narrow_row_hint(int(h))
         r = os.environ.get("ACMB200_MIXBWD_RING")
         if r is not None:
             lib.acm_set_mix_bwd_ring(int(r))

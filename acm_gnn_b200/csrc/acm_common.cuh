@@ -52,6 +52,41 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
   return v;
 }
 
+// relu of 8 packed bf16 values (4 HMNMX2 instead of 8 FMNMX after the unpack)
+__device__ __forceinline__ uint4 relu_bf16x8(uint4 v) {
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
+  return v;
+}
+
+// 8 consecutive floats from a 32-byte aligned shared-memory address as two LDS.128 (scalar reads
+// at a 32-byte lane stride are 8-way bank conflicts)
+__device__ __forceinline__ void load_smem8(const float* s, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(s);
+  const float4 b = *reinterpret_cast<const float4*>(s + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// 16-byte read-only load with the L2 prefetch-size hint pinned to 64 B (narrow-row gathers: a
+// 64-byte table row per edge, see acm_set_narrow_row_hint)
+__device__ __forceinline__ uint4 ldg_l2_64(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+// gather load of one slice: HINT = 1 -> L2::64B prefetch-size hint (narrow rows)
+template <int HINT, typename S, typename T>
+__device__ __forceinline__ void gather_load(S& s, const T* p) {
+  if (HINT) s.load_l2_64(p); else s.load(p);
+}
+
+extern int g_narrow_row_hint;   // csr.cu; set by acm_set_narrow_row_hint
+
 template <typename T>
 struct Slice8;  // raw (register) form of 8 consecutive features of storage type T
 
@@ -60,6 +95,7 @@ struct Slice8<__nv_bfloat16> {
   uint4 v;
   __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
   __device__ __forceinline__ void load_plain(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void load_l2_64(const __nv_bfloat16* p) { v = ldg_l2_64(p); }
   __device__ __forceinline__ void to_float(float* f) const { unpack_bf16x8(v, f); }
   __device__ __forceinline__ static void store(__nv_bfloat16* p, const float* f) {
     *reinterpret_cast<uint4*>(p) = pack_bf16x8(f);
@@ -77,6 +113,11 @@ struct Slice8<float> {
   __device__ __forceinline__ void load_plain(const float* p) {
     a = *reinterpret_cast<const float4*>(p);
     b = *(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void load_l2_64(const float* p) {
+    const uint4 x = ldg_l2_64(p), y = ldg_l2_64(p + 4);
+    a = make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w));
+    b = make_float4(__uint_as_float(y.x), __uint_as_float(y.y), __uint_as_float(y.z), __uint_as_float(y.w));
   }
   __device__ __forceinline__ void to_float(float* f) const {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;

@@ -22,6 +22,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int g_narrow_row_hint = 0;
 
 // rowptr[r] = first position e with row[e] >= r   (row sorted ascending)
 __global__ void rowptr_kernel(const int64_t* __restrict__ row, int64_t nnz, int64_t n, int64_t* __restrict__ rowptr) {
@@ -153,5 +154,10 @@ extern "C" int acm_cast_pad(const float* src, int64_t rows, int64_t cols, int64_
   else
     cast_pad_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(src, rows, cols, ld_src, (float*)dst, ld_dst);
   ACM_LAUNCH_CHECK("cast_pad");
+  return 0;
+}
+
+extern "C" int acm_set_narrow_row_hint(int on) {
+  acm::g_narrow_row_hint = on ? 1 : 0;
   return 0;
 }

@@ -190,8 +190,14 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
           G[0] = a.x; G[1] = a.y; G[2] = a.z; G[3] = a.w;
           G[4] = b.x; G[5] = b.y; G[6] = b.z; G[7] = b.w;
         }
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(d + 1024 + lane * 16), o[0]);
-        unpack_bf16x8(*reinterpret_cast<const uint4*>(d + 1536 + lane * 16), o[1]);
+        uint4 vl = *reinterpret_cast<const uint4*>(d + 1024 + lane * 16);
+        uint4 vh = *reinterpret_cast<const uint4*>(d + 1536 + lane * 16);
+        if (!p.variant) {   // o_lh may hold the pre-relu [S_L|S_H] (aggregate-first order): relu on load
+          vl = relu_bf16x8(vl);
+          vh = relu_bf16x8(vh);
+        }
+        unpack_bf16x8(vl, o[0]);
+        unpack_bf16x8(vh, o[1]);
         unpack_bf16x8(*reinterpret_cast<const uint4*>(d + 2048 + lane * 16), o[2]);
       }
       const int64_t rn = base0 + (it + kRingStages) * stride + warp * RPW + sub;
@@ -227,6 +233,13 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
       a.to_float(o[0]);
       b.to_float(o[1]);
       d.to_float(o[2]);
+      if (!p.variant) {     // see the ring path: o_lh may be the pre-relu table
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          o[0][t] = fmaxf(o[0][t], 0.f);
+          o[1][t] = fmaxf(o[1][t], 0.f);
+        }
+      }
     }
     if (valid) {
 #pragma unroll
@@ -272,10 +285,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
       if (!LN) {
+        float ak[8];
+        load_smem8(s_a + k * FP + f0, ak);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
           da[k][t] = fmaf(dz[k], o[k][t], da[k][t]);
-          dO[k][t] = fmaf(c * al[k], G[t], dz[k] * s_a[k * FP + f0 + t]);
+          dO[k][t] = fmaf(c * al[k], G[t], dz[k] * ak[t]);
         }
       } else {
         float s1 = 0.f;
@@ -289,18 +304,21 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
           s2 = fmaf(xh[t], xh[t], s2);
         }
         const float rstd = 1.f / sqrtf(group_sum<LANES>(s2) * inv_f + kLnEps);
-        float gx = 0.f;
+        float gx = 0.f, gak[8], ak[8];
+        load_smem8(s_gam + k * FP + f0, gak);
+        load_smem8(s_a + k * FP + f0, ak);
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
+          gak[t] *= ak[t];
           xh[t] *= rstd;
-          gx = fmaf(s_gam[k * FP + f0 + t] * s_a[k * FP + f0 + t], xh[t], gx);
+          gx = fmaf(gak[t], xh[t], gx);
         }
         const float m1 = dz[k] * s_sum[k] * inv_f;
         const float m2 = dz[k] * group_sum<LANES>(gx) * inv_f;
         dsum[k] += dz[k];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          const float ga = s_gam[k * FP + f0 + t] * s_a[k * FP + f0 + t];
+          const float ga = gak[t];
           da[k][t] = fmaf(dz[k], xh[t], da[k][t]);  // T_k
           const float dln = (f0 + t < p.f) ? rstd * (dz[k] * ga - m1 - xh[t] * m2) : 0.f;
           dO[k][t] = fmaf(c * al[k], G[t], dln);

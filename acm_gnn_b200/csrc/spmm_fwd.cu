@@ -83,7 +83,8 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-// GM: 0 register-staged LDG gather, 1 cp.async (LDGSTS) ring, 2 cp.async.bulk ring (FP = 256)
+// GM: 0 register-staged LDG gather, 1 cp.async (LDGSTS) ring, 2 cp.async.bulk ring (FP = 256),
+//     3 LDG gather with the L2::64B prefetch-size hint (narrow rows, FP <= 32)
 template <typename T, int FP, int MODE, int GM>
 __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t rb, const float* s_a,
                                               const float* s_avec, const float* s_ga, const float* s_sc,
@@ -229,8 +230,8 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const T* r = tab + (int64_t)c[u] * TW;
-      vl[u].load(r);
-      vh[u].load(r + FP);
+      gather_load<GM == 3>(vl[u], r);
+      gather_load<GM == 3>(vh[u], r + FP);
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -249,8 +250,8 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
     const float w = val ? __ldg(val + e) : 1.f;
     const T* r = tab + (int64_t)c * TW;
     Slice8<T> vl, vh;
-    vl.load(r);
-    vh.load(r + FP);
+    gather_load<GM == 3>(vl, r);
+    gather_load<GM == 3>(vh, r + FP);
     float fl[8], fh[8];
     vl.to_float(fl);
     vh.to_float(fh);
@@ -313,20 +314,23 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
   for (int k = 0; k < KMAX; ++k) {
     float dot = 0.f;
     if (!ln) {
+      float ak[8];
+      load_smem8(s_a + k * FP + gl * 8, ak);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) dot = fmaf(o[k][t], s_a[k * FP + gl * 8 + t], dot);
+      for (int t = 0; t < 8; ++t) dot = fmaf(o[k][t], ak[t], dot);
       z[k] = group_sum<LANES>(dot);
     } else {
       float s1 = 0.f;
 #pragma unroll
       for (int t = 0; t < 8; ++t) s1 += o[k][t];
       const float mu = group_sum<LANES>(s1) * inv_f;
-      float s2 = 0.f;
+      float s2 = 0.f, gak[8];
+      load_smem8(s_ga + k * FP + gl * 8, gak);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const float d = (gl * 8 + t < p.f) ? o[k][t] - mu : 0.f;
         s2 = fmaf(d, d, s2);
-        dot = fmaf(d, s_ga[k * FP + gl * 8 + t], dot);
+        dot = fmaf(d, gak[t], dot);
       }
       const float var = group_sum<LANES>(s2) * inv_f;
       dot = group_sum<LANES>(dot);
@@ -484,6 +488,9 @@ static int launch_fwd(const FwdParams& p, cudaStream_t st) {
     smem += (size_t)kFwdWarps * AsyncCfg<T>::kStages * 64 * 8 * sizeof(T);
     if (int rc = raise_smem(spmm_mix_fwd_kernel<T, FP, MODE, 1>, smem)) return rc;
     spmm_mix_fwd_kernel<T, FP, MODE, 1><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
+  } else if (FP <= 32 && !p.pre_agg && g_narrow_row_hint) {
+    constexpr int GMH = FP <= 32 ? 3 : 0;    // the hinted loop is only instantiated for narrow rows
+    spmm_mix_fwd_kernel<T, FP, MODE, GMH><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
   } else {
     spmm_mix_fwd_kernel<T, FP, MODE, 0><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
   }

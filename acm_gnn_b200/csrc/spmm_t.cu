@@ -14,7 +14,7 @@ namespace acm {
 constexpr int kTWarps = 8;
 constexpr int kTUnroll = 4;
 
-template <typename T, int FP>
+template <typename T, int FP, int HINT>
 __global__ void __launch_bounds__(kTWarps * 32)
 spmm_t_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
               const float* __restrict__ val, const T* __restrict__ table, const T* __restrict__ ptab,
@@ -53,8 +53,8 @@ spmm_t_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, 
 #pragma unroll
     for (int u = 0; u < kTUnroll; ++u) {
       const T* r = tab + (int64_t)c[u] * TW;
-      vl[u].load(r);
-      vh[u].load(r + FP);
+      gather_load<HINT>(vl[u], r);
+      gather_load<HINT>(vh[u], r + FP);
     }
 #pragma unroll
     for (int u = 0; u < kTUnroll; ++u) {
@@ -73,8 +73,8 @@ spmm_t_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, 
     const float w = val ? __ldg(val + e) : 1.f;
     const T* r = tab + (int64_t)c * TW;
     Slice8<T> vl, vh;
-    vl.load(r);
-    vh.load(r + FP);
+    gather_load<HINT>(vl, r);
+    gather_load<HINT>(vh, r + FP);
     float fl[8], fh[8];
     vl.to_float(fl);
     vh.to_float(fh);
@@ -370,8 +370,14 @@ extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
     constexpr int RPB = (32 / (FP / 8)) * kTWarps;                                                 \
     const int64_t blocks = (n_rows + RPB - 1) / RPB;                                               \
     ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_t_bwd: too many rows");                              \
-    spmm_t_kernel<TT, FP><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                              \
-        n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all, lr); \
+    if (FP <= 32 && g_narrow_row_hint) {                                                           \
+      constexpr int H = FP <= 32 ? 1 : 0;                                                          \
+      spmm_t_kernel<TT, FP, H><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                         \
+          n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all, lr); \
+    } else {                                                                                       \
+      spmm_t_kernel<TT, FP, 0><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                         \
+          n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all, lr); \
+    }                                                                                              \
   })
   if (dtype == ACM_BF16) { ACM_T_LAUNCH(__nv_bfloat16); } else { ACM_T_LAUNCH(float); }
 #undef ACM_T_LAUNCH

@@ -357,13 +357,17 @@ class AcmLayerFunction(torch.autograd.Function):
         y = torch.empty(n, f, dtype=torch.bfloat16 if y_bf16 else torch.float32, device=dev)
         att = torch.empty(n, K, dtype=torch.float32, device=dev)
         sig = torch.empty(n, K, dtype=torch.float32, device=dev) if need_grad else None
-        o_save = torch.empty(n, 2 * fp, dtype=tdt, device=dev) if need_grad else None
+        # aggregate-first: the table already holds [S_L|S_H] and O_k = relu(S_k), so the table itself is
+        # what the backward needs (mix_bwd applies the relu on load for variant 0) -- no second copy
+        o_save = torch.empty(n, 2 * fp, dtype=tdt, device=dev) if (need_grad and not agg_first) else None
         _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, row0, csr[0], csr[1], csr[2], 0,
                   table.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s), pack.data_ptr(),
                   K, int(cfg.ln_live), int(cfg.variant), float(cfg.out_scale),
                   y.data_ptr(), _lib.ACM_BF16 if y_bf16 else _lib.ACM_F32, f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig),
                   lr[0], lr[1], lr[2], st, tag=fp)
         del lr
+        if need_grad and agg_first:
+            o_save = h_lh
 
         ctx.mark_non_differentiable(att)
         if need_grad:

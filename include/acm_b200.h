@@ -198,7 +198,10 @@ int acm_set_gather_mode(int mode);
  * 185-204).  g = dL/dY [n_rows, f].  Writes t_lh [n_rows, 2*fp] = [dS_L | dS_H] (the table
  * the transposed aggregation gathers), dh_all[:, 2fp:3fp] = dHI, optional dos_pre (grad
  * of the structure channel before its relu) and atomically accumulates the parameter
- * gradients into dpack (same layout as pack; zeroed by caller). */
+ * gradients into dpack (same layout as pack; zeroed by caller).
+ * o_lh [n_rows, 2*fp]: variant 0 -> either the saved [O_L|O_H] or the pre-relu [S_L|S_H] (the
+ * kernel applies the relu on load, which is the identity on already-relu'd values: the
+ * aggregate-first order passes its [S_L|S_H] table and saves no second copy); variant 1 -> [O_L|O_H]. */
 int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
                 const void* g, int g_dtype, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
                 const float* att, const float* sig, const float* pack,
@@ -236,6 +239,13 @@ int acm_nll_log_softmax(const float* logits, int64_t ld, int64_t n_rows, int n_c
 /* cudaLimitMaxL2FetchGranularity (32/64/128 bytes) of the current device: narrow rows
  * (out_features <= 16 -> 64-byte table rows) over-fetch at the default granularity. */
 int acm_set_l2_fetch_granularity(int bytes);
+
+/* Narrow-row gathers (padded width <= 32: one 64..128-byte table row per stored edge, layer 1 of
+ * every reference model): 1 = issue the neighbour-row loads with the PTX L2::64B prefetch-size
+ * hint (ld.global.nc.L1::no_allocate.L2::64B) instead of plain read-only loads.  Results are
+ * bit-identical; the knob exists because the default fetch policy moves ~1.6x the algorithmic
+ * bytes through DRAM for these rows (profiles/README.md). */
+int acm_set_narrow_row_hint(int on);
 
 #ifdef __cplusplus
 }
