@@ -7,5 +7,6 @@ from .functional import AcmLayerFunction, LayerConfig, StagedInput, padded_width
 from .layers import MLP, GraphConvolution  # noqa: F401
 from .models import GCN  # noqa: F401
 from .operator import AcmOperator, CsrMatrix, cached_operator  # noqa: F401
+from .graphed import GraphedForward, GraphedTrainStep  # noqa: F401
 
 __version__ = "0.1.0"

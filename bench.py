@@ -61,6 +61,10 @@ def parse_args():
     ap.add_argument("--no-stage-input", action="store_true",
                     help="pass the raw fp32 feature tensor to the model every step (cast + all-gather inside the timed region) "
                          "instead of features staged once in the kernel layout")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the whole train step (zero_grad, fwd, loss, bwd, Adam) in ONE CUDA graph and time replays "
+                         "(acm_gnn_b200.graphed.GraphedTrainStep): for the launch-bound small graphs of BASELINE configs 1-4; "
+                         "single GPU; no per-kernel roofline (CUDA events cannot be recorded inside a capture)")
     ap.add_argument("--reorder", default=os.environ.get("ACMB200_REORDER", "auto"), choices=["off", "auto"],
                     help="aggregate-first order A(XW)=(AX)W for layers whose input needs no gradient (SURVEY 8f rank 4)")
     return ap.parse_args()
@@ -211,7 +215,7 @@ def workload_config(args, world):
             "skew": args.skew, "nodes": args.nodes, "edges": args.edges, "fin": args.fin, "hidden": args.hidden, "nclass": args.nclass,
             "step": "forward + log_softmax/NLL (" + ("torch glue" if args.torch_loss else "fused acm_nll_log_softmax") + ") + backward + Adam.step",
             "partition": f"1-D row partition over {world} GPU(s)" if world > 1 else "single GPU",
-            "input_staging": "raw fp32 features every step" if args.no_stage_input else "features staged once in the kernel layout (bf16, padded, all-gathered across ranks) before the timed region; e2e starts from host fp32 buffers every step",
+            "input_staging": "raw fp32 features every step" if (args.no_stage_input or args.graph or args.fin > 256) else "features staged once in the kernel layout (bf16, padded, all-gathered across ranks) before the timed region; e2e starts from host fp32 buffers every step",
             "l2": "inputs >> L2 (no flush)" if args.nodes * args.hidden * 2 > 4 * 126e6 else "L2 flushed between timed steps"}
 
 
@@ -287,9 +291,18 @@ def run_ours(args):
     if part is not None:
         attach(model, part)
     params = [p for k, p in model.named_parameters() if k not in ("fea_param", "xX_param")]
-    opt = torch.optim.Adam(params, lr=0.05, weight_decay=1e-3)  # reference defaults, arg_parser.py:51-53
+    if args.graph and world > 1:
+        raise SystemExit("--graph is single-GPU only")
+    # reference defaults, arg_parser.py:51-53 (capturable: optimizer state stays on the device for the graph capture)
+    opt = torch.optim.Adam(params, lr=0.05, weight_decay=1e-3, capturable=bool(args.graph))
+    gstep = None
 
     def step(xin, lab):
+        if gstep is not None:
+            if xin is not gstep.x:       # e2e: this step's inputs land in the graph's static tensors
+                gstep.x.copy_(xin, non_blocking=True)
+                gstep.labels.copy_(lab, non_blocking=True)
+            return gstep()
         model.train()
         opt.zero_grad(set_to_none=True)
         out = model(xin, op, None, None)
@@ -312,13 +325,16 @@ def run_ours(args):
     # features resident for the whole run.  `e2e` below starts from host fp32 buffers instead.
     from acm_gnn_b200.functional import stage_input
     x_value = x
-    if not args.no_stage_input and fin <= 256:
+    if not args.no_stage_input and fin <= 256 and not args.graph:
         x_value = stage_input(x, args.dtype, part)
 
     flush = None
     if args.nodes * args.hidden * 2 <= 4 * 126e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    if args.graph:
+        from acm_gnn_b200.graphed import GraphedTrainStep
+        gstep = GraphedTrainStep(model, opt, x_value, (op, None, None), labels, train_mask, warmup=3)
     for _ in range(args.warmup):
         step(x_value, labels)
     barrier()
@@ -353,6 +369,8 @@ def run_ours(args):
     barrier()
     total_ms = sum(s.elapsed_time(e) for s, e in spans)
     launches = _lib.launch_count() - launches0
+    if gstep is not None:
+        launches = gstep.launches_per_step * args.steps   # library launches captured in the graph x replays
     clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -410,7 +428,7 @@ def run_ours(args):
     # With --reorder auto layer 0 runs aggregate-first, so the fused gather kernel of layer 0 is timed here in a
     # short separate pass of full train steps in the transform-first order (same graph, inputs, parameters).
     north = None
-    if key_agg in summ:
+    if key_agg in summ and gstep is None:
         os.environ["ACMB200_REORDER"] = "off"
         k_ns = max(2, min(3, args.steps))
         step(x_value, labels)
@@ -521,7 +539,7 @@ def run_ours(args):
                 + ("through NVSwitch multicast (multimem.st)" if part.multicast else "peer mappings (unicast stores)"))),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches,
             "nnz": nnz_global, "max_degree": max_deg, "long_rows": n_long_rows, "peak_mem_gb": round(peak_mem, 2), "loss": final_loss,
-            "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first in layer 0 (A(XW)=(AX)W, SURVEY 8f rank 4), transform-first fused SpMM+mix in layer 1" if key_agg in summ else "transform-first (north-star fused SpMM+mix) in both layers",
+            "cuda_graph": bool(args.graph), "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first in layer 0 (A(XW)=(AX)W, SURVEY 8f rank 4), transform-first fused SpMM+mix in layer 1" if key_agg in summ else "transform-first (north-star fused SpMM+mix) in both layers",
             "north_star_order": north,
         }
         print(json.dumps(line), flush=True)

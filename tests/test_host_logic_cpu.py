@@ -129,3 +129,15 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(root, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_graphed_step_has_no_cpu_path():
+    """The CUDA-graph wrappers refuse CPU tensors like every other entry point (no fallback)."""
+    from acm_gnn_b200.graphed import GraphedForward, GraphedTrainStep
+    model = A.GCN(6, 8, 3, 2, 10, 0.0, "acmgcn", 0)
+    x = torch.rand(10, 6)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        GraphedForward(model, x, (None, None, None))
+    opt = torch.optim.SGD(model.parameters(), lr=0.1)
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        GraphedTrainStep(model, opt, x, (None, None, None), torch.zeros(10, dtype=torch.int64), torch.ones(10, dtype=torch.uint8))
