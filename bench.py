@@ -65,6 +65,9 @@ def parse_args():
                     help="capture the whole train step (zero_grad, fwd, loss, bwd, Adam) in ONE CUDA graph and time replays "
                          "(acm_gnn_b200.graphed.GraphedTrainStep): for the launch-bound small graphs of BASELINE configs 1-4; "
                          "single GPU; no per-kernel roofline (CUDA events cannot be recorded inside a capture)")
+    ap.add_argument("--ab-narrow-hint", action="store_true",
+                    help="after the timed region, time the narrow-row gather kernels (layer 1) with acm_set_narrow_row_hint off / on "
+                         "in the same process and report both under narrow_hint_ab")
     ap.add_argument("--reorder", default=os.environ.get("ACMB200_REORDER", "auto"), choices=["off", "auto"],
                     help="aggregate-first order A(XW)=(AX)W for layers whose input needs no gradient (SURVEY 8f rank 4)")
     return ap.parse_args()
@@ -148,18 +151,54 @@ class Clocks:
 # CPU oracle timing (cpu_baseline leg and --impl reference)
 # ----------------------------------------------------------------------------------------
 
+REF_PT = os.path.join(ROOT, "baseline", "_ref", "ACM-Pytorch")
+
+
+def reference_available():
+    """The UNMODIFIED reference modules staged under baseline/_ref by scripts/stage_reference.py
+    (git-ignored, shipped to the GPU box with the repo snapshot)."""
+    return os.path.exists(os.path.join(REF_PT, "models", "models.py")) and os.environ.get("ACMB200_BENCH_PORT", "0") != "1"
+
+
 def cpu_step_factory(n, e_directed, fin, hidden, nclass):
-    import numpy as np
+    """One CPU train step of the 2-layer acmgcn on a synthetic graph, as ``train_model`` does it
+    (ACM-Pytorch/utils.py:547-574: zero_grad, forward, log_softmax + nll_loss on the train rows,
+    backward, Adam.step), with both operators as sparse COO (the torch.sparse.mm path
+    BASELINE.json names; ACM-Geometric/train.py:77-80).  Returns (step, nnz, kind):
+    kind "reference" = the reference's own GCN module (models/models.py, layers.py) imported
+    unmodified from baseline/_ref; kind "port" = oracle/acm_oracle.py when it is not staged."""
     import torch
+    import torch.nn.functional as F
     from oracle import acm_oracle as O
     torch.set_num_threads(os.cpu_count())
     row, col = O.synthetic_edges(n, e_directed, seed=0)
     op = O.build_operator(row, col, n, "pytorch")
-    low, high = O.operator_to_torch(op)  # both sparse COO: the torch.sparse.mm path BASELINE.json names
+    low, high = O.operator_to_torch(op)  # both sparse COO
     g = torch.Generator().manual_seed(1)
     x = O.row_normalise_features(torch.rand(n, fin, generator=g))
     labels = torch.randint(0, nclass, (n,), generator=g)
     idx = torch.randperm(n, generator=g)[: int(0.6 * n)]
+    if reference_available():
+        if torch.cuda.is_available():
+            raise RuntimeError("the reference places its parameters on cuda:0 when a GPU is visible "
+                               "(models/layers.py:10-11): run the CPU arm with CUDA_VISIBLE_DEVICES=''")
+        sys.path.insert(0, REF_PT)
+        from models.models import GCN as RefGCN   # the reference's own file, unmodified
+        torch.manual_seed(42)
+        model = RefGCN(nfeat=fin, nhid=hidden, nclass=nclass, nlayers=2, nnodes=n, dropout=0.0,
+                       model_type="acmgcn", structure_info=0, variant=False)
+        ropt = torch.optim.Adam(model.parameters(), lr=0.05, weight_decay=1e-3)
+
+        def ref_step():
+            model.train()
+            ropt.zero_grad()
+            out = F.log_softmax(model(x, low, high, None), dim=1)
+            loss = F.nll_loss(out[idx], labels[idx])
+            loss.backward()
+            ropt.step()
+            return float(loss.item())
+
+        return ref_step, op.nnz, "reference"
     gp = torch.Generator().manual_seed(42)
     params = O.init_gcn_params(fin, hidden, nclass, 0, "acmgcn", 0, gp)
     leaves = [t.requires_grad_(True) for grp in params.values() for k, t in grp.items() if not k.startswith(("layer_norm", "struc", "att_struc"))]
@@ -171,40 +210,65 @@ def cpu_step_factory(n, e_directed, fin, hidden, nclass):
         loss = O.train_step_loss(out, labels, idx)
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
-    return step, op.nnz
+    return step, op.nnz, "port"
 
 
 def time_cpu(steps, warmup, n, args):
     e = int(round(args.edges * (n / args.nodes)))
-    step, nnz = cpu_step_factory(n, e, args.fin, args.hidden, args.nclass)
+    step, nnz, kind = cpu_step_factory(n, e, args.fin, args.hidden, args.nclass)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return nnz / dt, dt * 1e3, nnz
+    return nnz / dt, dt * 1e3, nnz, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # CPU arm: hide the GPUs before torch is imported (the reference's modules place parameters on
+    # cuda:0 whenever one is visible, models/layers.py:10-11)
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
     n = min(args.cpu_nodes, args.nodes)
-    val, ms, nnz = time_cpu(args.steps, args.warmup, n, args)
-    sample = (f"CPU oracle (torch.sparse.mm COO, fp32) full train step on a scaled graph N={n}, nnz={nnz} "
-              f"(same mean degree and widths as the {args.nodes}-node workload)")
+    val, ms, nnz, kind = time_cpu(args.steps, args.warmup, n, args)
+    sample = (("the reference's own GCN module (baseline/_ref/ACM-Pytorch/models, unmodified)" if kind == "reference"
+               else "CPU oracle port (oracle/acm_oracle.py)")
+              + f", torch.sparse.mm COO operators, fp32, full train step on a scaled graph N={n}, nnz={nnz} "
+              f"(same mean degree and widths as the {args.nodes}-node workload), {ms:.0f} ms/step")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """cpu_baseline leg of the GPU arm: the reference arm of this same file in a child process
+    with the GPUs hidden (the reference modules pick cuda:0 at import time whenever one is
+    visible), 1 warm-up + 2 timed steps on the bounded sample."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--nodes", str(args.nodes), "--edges", str(args.edges), "--fin", str(args.fin), "--hidden", str(args.hidden),
+           "--nclass", str(args.nclass), "--cpu-nodes", str(args.cpu_nodes)]
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        cb = line["cpu_baseline"]
+        cb["sample"] += "; 1 warm-up + 2 timed steps"
+        return cb
+    except Exception as e:  # a reported baseline: never fail the GPU measurement over it
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"cpu baseline failed: {e!r}"}
 
 
 def workload_config(args, world):
@@ -332,7 +396,23 @@ def run_ours(args):
     if args.nodes * args.hidden * 2 <= 4 * 126e6:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    eager_ms = None
     if args.graph:
+        # the same step launched eagerly (one host launch per kernel), timed the same way, for comparison
+        for _ in range(args.warmup):
+            step(x_value, labels)
+        barrier()
+        tot = 0.0
+        for _ in range(args.steps):
+            if flush is not None:
+                flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step(x_value, labels)
+            b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        eager_ms = tot / args.steps
         from acm_gnn_b200.graphed import GraphedTrainStep
         gstep = GraphedTrainStep(model, opt, x_value, (op, None, None), labels, train_mask, warmup=3)
     for _ in range(args.warmup):
@@ -465,6 +545,24 @@ def run_ours(args):
                                   "frac": ach / roof["peak"] if roof else None, "traffic": tr,
                                   "algorithmic_bytes_per_launch": ab, "avg_launch_ms": ms / cnt, "launches_timed": cnt}}
 
+    # ---- A/B of the narrow-row gather hint (layer 1: 64-byte table rows) in the same process ----
+    hint_ab = None
+    if args.ab_narrow_hint and gstep is None:
+        hint_ab = {}
+        for hint in (0, 1):
+            _lib.call("acm_set_narrow_row_hint", hint)
+            step(x_value, labels)
+            barrier()
+            t_ab = _lib.KernelTimer()
+            _lib.set_timer(t_ab)
+            for _ in range(3):
+                step(x_value, labels)
+            _lib.set_timer(None)
+            barrier()
+            hint_ab["on" if hint else "off"] = {k: round(v[1] / 3, 4) for k, v in sorted(t_ab.summary().items())
+                                                if k.startswith(("acm_spmm_mix_fwd", "acm_spmm_t_bwd", "acm_mix_bwd"))}
+        _lib.call("acm_set_narrow_row_hint", int(os.environ.get("ACMB200_NARROW_HINT", "0")))
+
     # ---- end to end through the public module API with HOST buffers ---------------------------
     e2e = None
     if not args.no_e2e:
@@ -522,10 +620,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ncpu = min(args.cpu_nodes, n)
-        v, ms_c, nnz_c = time_cpu(2, 1, ncpu, args)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-               "sample": f"CPU oracle (torch.sparse.mm COO path, fp32) train step on scaled graph N={ncpu}, nnz={nnz_c}, same mean degree/widths; 1 warm-up + 2 timed steps, {ms_c:.0f} ms/step"}
+        cpu = cpu_baseline_subprocess(args)
 
     if rank == 0:
         line = {
@@ -539,7 +634,8 @@ def run_ours(args):
                 + ("through NVSwitch multicast (multimem.st)" if part.multicast else "peer mappings (unicast stores)"))),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches,
             "nnz": nnz_global, "max_degree": max_deg, "long_rows": n_long_rows, "peak_mem_gb": round(peak_mem, 2), "loss": final_loss,
-            "cuda_graph": bool(args.graph), "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first in layer 0 (A(XW)=(AX)W, SURVEY 8f rank 4), transform-first fused SpMM+mix in layer 1" if key_agg in summ else "transform-first (north-star fused SpMM+mix) in both layers",
+            "cuda_graph": bool(args.graph), "eager_ms_per_step": eager_ms, "narrow_hint_ab": hint_ab,
+            "narrow_row_hint": int(os.environ.get("ACMB200_NARROW_HINT", "0")), "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first in layer 0 (A(XW)=(AX)W, SURVEY 8f rank 4), transform-first fused SpMM+mix in layer 1" if key_agg in summ else "transform-first (north-star fused SpMM+mix) in both layers",
             "north_star_order": north,
         }
         print(json.dumps(line), flush=True)

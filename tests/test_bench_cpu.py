@@ -24,10 +24,18 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "edges/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == os.cpu_count()
+    staged = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "ACM-Pytorch", "models", "models.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert d["cpu_baseline"]["cores"] == os.cpu_count()
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and d["metric"] == "acm_gcn_train_step_edges_per_sec"
 
 
 def test_reference_arm_nonzero_rank_is_silent():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, ("--gpus", "2")) == []
+
+
+def test_reference_arm_falls_back_to_the_oracle_port():
+    """Without the staged reference tree (forced here) the CPU arm times oracle/acm_oracle.py."""
+    d = json.loads(_run({"ACMB200_BENCH_PORT": "1"})[0])
+    assert d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
