@@ -22,7 +22,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
-int g_narrow_row_hint = 0;
+int g_narrow_row_hint = 1;   // default on: measured 1-5 % faster on the layer-1 gathers, bit-identical
 
 // rowptr[r] = first position e with row[e] >= r   (row sorted ascending)
 __global__ void rowptr_kernel(const int64_t* __restrict__ row, int64_t nnz, int64_t n, int64_t* __restrict__ rowptr) {

@@ -164,9 +164,30 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
   // staging tile of the narrow-row peer push
   T* push_stage = (p.peers.n > 0 && LANES < 32) ? reinterpret_cast<T*>(tail) : nullptr;
 
+  // att / sig of a row (2K floats) are prefetched ONE iteration ahead, one float per lane: lane j of
+  // the row's group loads att[j] (j < K) or sig[j - K] (K <= j < 2K), and the values are broadcast
+  // by shuffle where they are used.  Loaded in place they were a dependent DRAM-latency stall per
+  // row that nothing but the other 3 warps of the scheduler could hide.
+  constexpr bool AS_PF = LANES >= 8;
+  float as_nxt = 0.f;
+  auto as_load = [&](const int64_t r) -> float {
+    if (gl < K) return __ldg(p.att + r * K + gl);
+    if (gl < 2 * K) return __ldg(p.sig + r * K + (gl - K));
+    return 0.f;
+  };
+  if (AS_PF && n_iter > 0) {
+    const int64_t r = base0 + warp * RPW + sub;
+    if (r < p.n_rows) as_nxt = as_load(r);
+  }
+
   for (int64_t it = 0; it < n_iter; ++it) {
     const int64_t row = base0 + it * stride + warp * RPW + sub;
     const bool valid = row < p.n_rows;
+    const float as_cur = as_nxt;
+    if (AS_PF) {
+      as_nxt = 0.f;
+      if (it + 1 < n_iter && row + stride < p.n_rows) as_nxt = as_load(row + stride);
+    }
     float G[8], o[KMAX][8], al[KMAX], sg[KMAX];
 #pragma unroll
     for (int t = 0; t < 8; ++t) G[t] = 0.f;
@@ -249,10 +270,19 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
         s4.load(reinterpret_cast<const T*>(p.o_s) + row * FP + f0);
         s4.to_float(o[KMAX - 1]);
       }
+      if (!AS_PF) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          al[k] = __ldg(p.att + row * K + k);
+          sg[k] = __ldg(p.sig + row * K + k);
+        }
+      }
+    }
+    if (AS_PF) {   // all lanes shuffle (invalid rows carry zeros, as the in-place loads left them)
 #pragma unroll
       for (int k = 0; k < KMAX; ++k) {
-        al[k] = __ldg(p.att + row * K + k);
-        sg[k] = __ldg(p.sig + row * K + k);
+        al[k] = __shfl_sync(0xffffffffu, as_cur, sub * LANES + k);
+        sg[k] = __shfl_sync(0xffffffffu, as_cur, sub * LANES + K + k);
       }
     }
     // d_alpha

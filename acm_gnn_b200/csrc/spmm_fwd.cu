@@ -83,8 +83,121 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// ---- epilogue: attention (optional LayerNorm, sigmoid, KxK mix, softmax), weighted sum, stores ----
+// o[k][t]: the channel outputs O_k of this lane's 8 features (already relu'd as the variant asks;
+// zeros for invalid rows).  Every lane of the warp must call it (group shuffles).
+template <typename T, int FP, int MODE>
+__device__ __forceinline__ void fwd_epilogue(const FwdParams& p, const int64_t row, const bool valid, const int gl,
+                                             float (&o)[(MODE & 2) ? 4 : 3][8], const float* s_a,
+                                             const float* s_avec, const float* s_ga, const float* s_sc) {
+  constexpr int LANES = FP / 8;
+  constexpr bool LN = (MODE & 1) != 0;
+  constexpr int KMAX = (MODE & 2) ? 4 : 3;
+  constexpr int K = KMAX;
+  constexpr int TW = 2 * FP;
+  float z[KMAX];
+  constexpr bool ln = LN;
+  const float inv_f = 1.f / (float)p.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    float dot = 0.f;
+    if (!ln) {
+      float ak[8];
+      load_smem8(s_a + k * FP + gl * 8, ak);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) dot = fmaf(o[k][t], ak[t], dot);
+      z[k] = group_sum<LANES>(dot);
+    } else {
+      float s1 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) s1 += o[k][t];
+      const float mu = group_sum<LANES>(s1) * inv_f;
+      float s2 = 0.f, gak[8];
+      load_smem8(s_ga + k * FP + gl * 8, gak);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float d = (gl * 8 + t < p.f) ? o[k][t] - mu : 0.f;
+        s2 = fmaf(d, d, s2);
+        dot = fmaf(d, gak[t], dot);
+      }
+      const float var = group_sum<LANES>(s2) * inv_f;
+      dot = group_sum<LANES>(dot);
+      z[k] = dot / sqrtf(var + kLnEps) + s_sc[k];
+    }
+  }
+  float s[KMAX], a[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) s[k] = sigmoidf_acc(z[k]);
+  float mx = -INFINITY;
+  const float inv_k = 1.f / (float)K;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j < K) l = fmaf(s[j], s_avec[j * 4 + k], l);
+    a[k] = (k < K) ? l * inv_k : -INFINITY;
+    mx = fmaxf(mx, a[k]);
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    a[k] = (k < K) ? expf(a[k] - mx) : 0.f;
+    den += a[k];
+  }
+  const float rden = 1.f / den;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) a[k] *= rden;
+
+  if (!valid) return;
+
+  float yv[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    float acc = a[0] * o[0][t];
+#pragma unroll
+    for (int k = 1; k < KMAX; ++k) acc = fmaf(a[k], o[k][t], acc);
+    yv[t] = p.out_scale * acc;
+  }
+  const int f0 = gl * 8;
+  if (p.y_bf16) {
+    // bf16 inter-layer activations (SURVEY 8f rank 3: the next layer's bf16 cast folded in here)
+    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + f0;
+    if (p.vec_y && f0 + 8 <= p.f) {
+      *reinterpret_cast<uint4*>(yb) = pack_bf16x8(yv);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 8; ++t)
+        if (f0 + t < p.f) yb[t] = __float2bfloat16_rn(yv[t]);
+    }
+  }
+  float* yr = p.y + row * p.ldy + f0;
+  if (p.y_bf16) {
+  } else if (p.vec_y && f0 + 8 <= p.f) {
+    *reinterpret_cast<float4*>(yr) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+    *reinterpret_cast<float4*>(yr + 4) = make_float4(yv[4], yv[5], yv[6], yv[7]);
+  } else {
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      if (f0 + t < p.f) yr[t] = yv[t];
+  }
+  if (p.o_save) {
+    T* os = reinterpret_cast<T*>(p.o_save) + row * TW + f0;
+    Slice8<T>::store(os, o[0]);
+    Slice8<T>::store(os + FP, o[1]);
+  }
+  if (gl == 0) {
+    for (int k = 0; k < K; ++k) {
+      p.att[row * K + k] = a[k];
+      if (p.sig) p.sig[row * K + k] = s[k];
+    }
+  }
+}
+
 // GM: 0 register-staged LDG gather, 1 cp.async (LDGSTS) ring, 2 cp.async.bulk ring (FP = 256),
-//     3 LDG gather with the L2::64B prefetch-size hint (narrow rows, FP <= 32)
+//     3 LDG gather with the L2::64B prefetch-size hint (narrow rows, FP <= 32),
+//     4 no gather at all: pre-aggregated mode (own kernel instantiation, so that its prefetch
+//       registers do not count against the occupancy of the gather kernels)
 template <typename T, int FP, int MODE, int GM>
 __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t rb, const float* s_a,
                                               const float* s_avec, const float* s_ga, const float* s_sc,
@@ -104,7 +217,7 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
   const bool valid = row < p.n_rows;
 
   int64_t e = 0, e1 = 0;
-  if (valid && !p.pre_agg) {
+  if (valid) {
     e = __ldg(p.rowptr + row);
     e1 = __ldg(p.rowptr + row + 1);
   }
@@ -272,12 +385,6 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
       b.load(reinterpret_cast<const T*>(p.h_i) + row * FP + gl * 8);
       a.to_float(hs);
       b.to_float(hi);
-      if (p.pre_agg) {
-        // aggregate-first order: the table row already holds [S_L | S_H] = [(AX)W_L | (X-AX)W_H]
-        Slice8<T> c;
-        c.load(tab + (p.row0 + row) * TW);
-        c.to_float(accL);
-      }
     } else {
 #pragma unroll
       for (int t = 0; t < 8; ++t) hs[t] = hi[t] = 0.f;
@@ -286,7 +393,7 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       float sl = rs * accL[t];
-      float sh = hs[t] - rs * accH[t];  // pre_agg: accH == 0, so S_H = table value
+      float sh = hs[t] - rs * accH[t];
       if (!p.variant) {
         sl = fmaxf(sl, 0.f);
         sh = fmaxf(sh, 0.f);
@@ -307,107 +414,11 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
     }
   }
 
-  float z[KMAX];
-  constexpr bool ln = LN;
-  const float inv_f = 1.f / (float)p.f;
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    float dot = 0.f;
-    if (!ln) {
-      float ak[8];
-      load_smem8(s_a + k * FP + gl * 8, ak);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) dot = fmaf(o[k][t], ak[t], dot);
-      z[k] = group_sum<LANES>(dot);
-    } else {
-      float s1 = 0.f;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) s1 += o[k][t];
-      const float mu = group_sum<LANES>(s1) * inv_f;
-      float s2 = 0.f, gak[8];
-      load_smem8(s_ga + k * FP + gl * 8, gak);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const float d = (gl * 8 + t < p.f) ? o[k][t] - mu : 0.f;
-        s2 = fmaf(d, d, s2);
-        dot = fmaf(d, gak[t], dot);
-      }
-      const float var = group_sum<LANES>(s2) * inv_f;
-      dot = group_sum<LANES>(dot);
-      z[k] = dot / sqrtf(var + kLnEps) + s_sc[k];
-    }
-  }
-  float s[KMAX], a[KMAX];
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) s[k] = sigmoidf_acc(z[k]);
-  float mx = -INFINITY;
-  const float inv_k = 1.f / (float)K;
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    float l = 0.f;
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j)
-      if (j < K) l = fmaf(s[j], s_avec[j * 4 + k], l);
-    a[k] = (k < K) ? l * inv_k : -INFINITY;
-    mx = fmaxf(mx, a[k]);
-  }
-  float den = 0.f;
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) {
-    a[k] = (k < K) ? expf(a[k] - mx) : 0.f;
-    den += a[k];
-  }
-  const float rden = 1.f / den;
-#pragma unroll
-  for (int k = 0; k < KMAX; ++k) a[k] *= rden;
-
-  if (!valid) return;
-
-  float yv[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    float acc = a[0] * o[0][t];
-#pragma unroll
-    for (int k = 1; k < KMAX; ++k) acc = fmaf(a[k], o[k][t], acc);
-    yv[t] = p.out_scale * acc;
-  }
-  const int f0 = gl * 8;
-  if (p.y_bf16) {
-    // bf16 inter-layer activations (SURVEY 8f rank 3: the next layer's bf16 cast folded in here)
-    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + f0;
-    if (p.vec_y && f0 + 8 <= p.f) {
-      *reinterpret_cast<uint4*>(yb) = pack_bf16x8(yv);
-    } else {
-#pragma unroll
-      for (int t = 0; t < 8; ++t)
-        if (f0 + t < p.f) yb[t] = __float2bfloat16_rn(yv[t]);
-    }
-  }
-  float* yr = p.y + row * p.ldy + f0;
-  if (p.y_bf16) {
-  } else if (p.vec_y && f0 + 8 <= p.f) {
-    *reinterpret_cast<float4*>(yr) = make_float4(yv[0], yv[1], yv[2], yv[3]);
-    *reinterpret_cast<float4*>(yr + 4) = make_float4(yv[4], yv[5], yv[6], yv[7]);
-  } else {
-#pragma unroll
-    for (int t = 0; t < 8; ++t)
-      if (f0 + t < p.f) yr[t] = yv[t];
-  }
-  if (p.o_save) {
-    T* os = reinterpret_cast<T*>(p.o_save) + row * TW + f0;
-    Slice8<T>::store(os, o[0]);
-    Slice8<T>::store(os + FP, o[1]);
-  }
-  if (gl == 0) {
-    for (int k = 0; k < K; ++k) {
-      p.att[row * K + k] = a[k];
-      if (p.sig) p.sig[row * K + k] = s[k];
-    }
-  }
+  fwd_epilogue<T, FP, MODE>(p, row, valid, gl, o, s_a, s_avec, s_ga, s_sc);
 }
 
 template <typename T, int FP, int MODE, int GM>
-__global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kFwdWarps * 32, GM == 4 ? 3 : 1) spmm_mix_fwd_kernel(const FwdParams p) {
   constexpr bool LN = (MODE & 1) != 0;
   constexpr int KMAX = (MODE & 2) ? 4 : 3;
 
@@ -427,12 +438,63 @@ __global__ void __launch_bounds__(kFwdWarps * 32) spmm_mix_fwd_kernel(const FwdP
   __syncthreads();
 
   constexpr int RPWk = 32 / (FP / 8);
-  if (p.pre_agg) {
-    // pre-aggregated (aggregate-first) mode: a block's rows are too little work to amortise the
-    // parameter-pack load above -> grid-stride over row blocks
+  if constexpr (GM == 4) {
+    // pre-aggregated (aggregate-first) mode: the own rows of `table` hold [S_L|S_H]; no gather, pure
+    // streaming.  A block's rows are too little work to amortise the parameter-pack load above ->
+    // grid-stride over row blocks, with the NEXT row's three slices prefetched into registers
+    // before the epilogue of the current one (without it each warp exposes a full DRAM latency
+    // per row: 3.6 TB/s measured; the epilogue is ~300 instructions deep).
+    constexpr int LANESk = FP / 8;
+    constexpr bool K4k = (MODE & 2) != 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sub = lane / LANESk, gl = lane % LANESk;
+    const T* tab = reinterpret_cast<const T*>(p.table) + gl * 8;
+    const T* hib = reinterpret_cast<const T*>(p.h_i) + gl * 8;
+    const T* osb = reinterpret_cast<const T*>(p.o_s) + gl * 8;
     const int64_t n_blocks = (p.n_rows + (int64_t)kFwdWarps * RPWk - 1) / ((int64_t)kFwdWarps * RPWk);
-    for (int64_t rb = blockIdx.x; rb < n_blocks; rb += gridDim.x)
-      fwd_row_block<T, FP, MODE, 0>(p, rb, s_a, s_avec, s_ga, s_sc, nullptr);
+    Slice8<T> nL, nH, nI, nS;
+    int64_t nrow = 0;
+    bool nvalid = false;
+    auto fetch = [&](const int64_t rb) {
+      nrow = (rb * kFwdWarps + warp) * RPWk + sub;
+      nvalid = nrow < p.n_rows;
+      if (nvalid) {
+        const T* r = tab + (p.row0 + nrow) * (2 * FP);
+        nL.load(r);
+        nH.load(r + FP);
+        nI.load(hib + nrow * FP);
+        if (K4k) nS.load(osb + nrow * FP);
+      }
+    };
+    int64_t rb = blockIdx.x;
+    if (rb < n_blocks) fetch(rb);
+    for (; rb < n_blocks; rb += gridDim.x) {
+      const Slice8<T> cL = nL, cH = nH, cI = nI, cS = nS;
+      const int64_t row = nrow;
+      const bool valid = nvalid;
+      if (rb + gridDim.x < n_blocks) fetch(rb + gridDim.x);
+      float o[KMAX][8];
+      if (valid) {
+        cL.to_float(o[0]);
+        cH.to_float(o[1]);
+        cI.to_float(o[2]);
+        if (K4k) cS.to_float(o[KMAX - 1]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          if (!p.variant) {
+            o[0][t] = fmaxf(o[0][t], 0.f);
+            o[1][t] = fmaxf(o[1][t], 0.f);
+          }
+          o[2][t] = fmaxf(o[2][t], 0.f);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+#pragma unroll
+          for (int t = 0; t < 8; ++t) o[k][t] = 0.f;
+      }
+      fwd_epilogue<T, FP, MODE>(p, row, valid, gl, o, s_a, s_avec, s_ga, s_sc);
+    }
   } else {
     // gather mode: one row block per CTA; the hardware block scheduler balances the degrees
     // the cp.async ring follows the parameter pack in dynamic shared memory (16-byte aligned)
@@ -475,7 +537,7 @@ static int launch_fwd(const FwdParams& p, cudaStream_t st) {
   // the ring pays off for wide rows (FP = 256: 97 % vs 91 % of HBM peak); for narrow rows (FP = 16,
   // two lanes per row) the per-edge commit/wait overhead costs more than it hides (measured 5.4 vs
   // 4.8 ms), so they keep the register-staged LDG loop
-  const int gm = p.pre_agg ? 0
+  const int gm = p.pre_agg ? 4
                  : (g_gather_mode == 2 && FP == 256) ? 2
                  : (g_gather_mode >= 1 && FP >= 64) ? 1 : 0;
   size_t smem = sizeof(float) * ((kPackFloats + 3) & ~3);
@@ -488,7 +550,9 @@ static int launch_fwd(const FwdParams& p, cudaStream_t st) {
     smem += (size_t)kFwdWarps * AsyncCfg<T>::kStages * 64 * 8 * sizeof(T);
     if (int rc = raise_smem(spmm_mix_fwd_kernel<T, FP, MODE, 1>, smem)) return rc;
     spmm_mix_fwd_kernel<T, FP, MODE, 1><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
-  } else if (FP <= 32 && !p.pre_agg && g_narrow_row_hint) {
+  } else if (gm == 4) {
+    spmm_mix_fwd_kernel<T, FP, MODE, 4><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
+  } else if (FP <= 32 && g_narrow_row_hint) {
     constexpr int GMH = FP <= 32 ? 3 : 0;    // the hinted loop is only instantiated for narrow rows
     spmm_mix_fwd_kernel<T, FP, MODE, GMH><<<(unsigned)blocks, kFwdWarps * 32, smem, st>>>(p);
   } else {
@@ -531,6 +595,7 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
   p.y_bf16 = (y_dtype == ACM_BF16);
   p.att = att; p.sig = sig;
   p.pre_agg = (rowptr == nullptr);
+  ACM_CHECK_ARG(!p.pre_agg || (rowscale == nullptr && n_long == 0), "spmm_mix_fwd: the pre-aggregated mode takes no rowscale / long rows");
   p.lr.rows = n_long > 0 ? long_rows : nullptr; p.lr.acc = long_acc; p.lr.n_long = n_long;
   ACM_CHECK_ARG(n_long == 0 || (long_rows && long_acc), "spmm_mix_fwd: long rows need long_rows and long_acc");
   p.vec_y = p.y_bf16 ? ((f % 8 == 0) && (ldy % 8 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0))

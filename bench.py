@@ -561,7 +561,7 @@ def run_ours(args):
             barrier()
             hint_ab["on" if hint else "off"] = {k: round(v[1] / 3, 4) for k, v in sorted(t_ab.summary().items())
                                                 if k.startswith(("acm_spmm_mix_fwd", "acm_spmm_t_bwd", "acm_mix_bwd"))}
-        _lib.call("acm_set_narrow_row_hint", int(os.environ.get("ACMB200_NARROW_HINT", "0")))
+        _lib.call("acm_set_narrow_row_hint", int(os.environ.get("ACMB200_NARROW_HINT", "1")))
 
     # ---- end to end through the public module API with HOST buffers ---------------------------
     e2e = None
@@ -635,7 +635,7 @@ def run_ours(args):
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clk, "gpu_launches": launches,
             "nnz": nnz_global, "max_degree": max_deg, "long_rows": n_long_rows, "peak_mem_gb": round(peak_mem, 2), "loss": final_loss,
             "cuda_graph": bool(args.graph), "eager_ms_per_step": eager_ms, "narrow_hint_ab": hint_ab,
-            "narrow_row_hint": int(os.environ.get("ACMB200_NARROW_HINT", "0")), "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first in layer 0 (A(XW)=(AX)W, SURVEY 8f rank 4), transform-first fused SpMM+mix in layer 1" if key_agg in summ else "transform-first (north-star fused SpMM+mix) in both layers",
+            "narrow_row_hint": int(os.environ.get("ACMB200_NARROW_HINT", "1")), "kernel_ms_per_step": breakdown, "gemm_impl": args.gemm, "l2_fetch": args.l2_fetch, "order": "aggregate-first in layer 0 (A(XW)=(AX)W, SURVEY 8f rank 4), transform-first fused SpMM+mix in layer 1" if key_agg in summ else "transform-first (north-star fused SpMM+mix) in both layers",
             "north_star_order": north,
         }
         print(json.dumps(line), flush=True)

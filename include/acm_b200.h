@@ -242,9 +242,9 @@ int acm_set_l2_fetch_granularity(int bytes);
 
 /* Narrow-row gathers (padded width <= 32: one 64..128-byte table row per stored edge, layer 1 of
  * every reference model): 1 = issue the neighbour-row loads with the PTX L2::64B prefetch-size
- * hint (ld.global.nc.L1::no_allocate.L2::64B) instead of plain read-only loads.  Results are
- * bit-identical; the knob exists because the default fetch policy moves ~1.6x the algorithmic
- * bytes through DRAM for these rows (profiles/README.md). */
+ * hint (ld.global.nc.L1::no_allocate.L2::64B) instead of plain read-only loads (default: 1).
+ * Results are bit-identical.  Background: these rows move ~1.6x their algorithmic bytes through
+ * DRAM (profiles/README.md); the hint recovers 1-5 % of the two layer-1 gather kernels. */
 int acm_set_narrow_row_hint(int on);
 
 #ifdef __cplusplus

@@ -3,12 +3,12 @@
 # headline bench with the in-process narrow-hint A/B, and graph-vs-eager on the small config shapes.
 set -u
 mkdir -p gpurun_out
-echo "=== pytest gpu" ; timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_r25.log 2>&1 ; echo "pytest rc=$?" ; tail -5 gpurun_out/pytest_gpu_r25.log
-echo "=== smoke" ; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r25.log 2>&1 ; echo "smoke rc=$?" ; tail -3 gpurun_out/smoke_r25.log
-echo "=== bench 10M default + narrow-hint A/B" ; timeout 900 python bench.py --steps 6 --no-cpu-baseline --no-e2e --ab-narrow-hint > gpurun_out/bench_10m_r25.log 2>&1 ; echo "rc=$?" ; tail -1 gpurun_out/bench_10m_r25.log | python -c "
+echo "=== pytest gpu" ; timeout 420 python -m pytest tests -q -m gpu --timeout 150 > gpurun_out/pytest_gpu_r25.log 2>&1 ; echo "pytest rc=$?" ; tail -5 gpurun_out/pytest_gpu_r25.log
+echo "=== smoke" ; timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r25.log 2>&1 ; echo "smoke rc=$?" ; tail -3 gpurun_out/smoke_r25.log
+echo "=== bench 10M default + narrow-hint A/B" ; timeout 330 python bench.py --steps 6 --no-cpu-baseline --no-e2e --ab-narrow-hint > gpurun_out/bench_10m_r25.log 2>&1 ; echo "rc=$?" ; tail -1 gpurun_out/bench_10m_r25.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['peak_mem_gb'], d['loss']); print(d['roofline']); print(d['kernel_ms_per_step']); print('AB', d['narrow_hint_ab']); print('north', d['north_star_order']['ms_per_step'], d['north_star_order']['roofline']['frac'])"
-run() { name=$1; shift; timeout 600 python bench.py --no-cpu-baseline --no-e2e --steps 20 "$@" > gpurun_out/bench_$name.log 2>&1; echo "$name rc=$?"; tail -1 gpurun_out/bench_$name.log | python -c "
+run() { name=$1; shift; timeout 150 python bench.py --no-cpu-baseline --no-e2e --steps 20 "$@" > gpurun_out/bench_$name.log 2>&1; echo "$name rc=$?"; tail -1 gpurun_out/bench_$name.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('  ms', round(d['ms_per_step'],4), 'eager ms', d.get('eager_ms_per_step'), 'edges/s', round(d['value']/1e6,1), 'M launches', d['gpu_launches'], 'loss', d['loss'])"; }
 run cfg1_cora_shape_graph --graph --nodes 2708 --edges 10556 --fin 1433 --hidden 64 --nclass 7
