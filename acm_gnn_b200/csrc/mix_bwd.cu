@@ -47,12 +47,16 @@ constexpr int kBwdWarps = 8;
 // into shared memory, so ~4 rows per group are in flight instead of the one row that the ~125
 // registers of this kernel leave room for (measured 9.8 -> 7.7 ms at the headline config).
 constexpr int kRingStages = 4;
-constexpr int kRingStageBytes = 32 * (32 + 3 * 16);   // per warp: G (<=32 B/lane) | O_L | O_H | HI (16 B/lane each)
+constexpr int kRingAsOff = 32 * (32 + 3 * 16);        // per warp: G (<=32 B/lane) | O_L | O_H | HI (16 B/lane each)
+constexpr int kRingStageBytes = kRingAsOff + 4 * 32;  // ... | per row group: att[0..3] (16 B) sig[0..3] (16 B), <= 4 groups
 
 __device__ __forceinline__ void bwd_cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void bwd_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bwd_cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
 template <int N> __device__ __forceinline__ void bwd_cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
@@ -67,7 +71,10 @@ struct BwdSmem {
 };
 
 // MINB = minimum resident CTAs per SM asked of ptxas (2: ~125 registers, no spills)
-template <typename T, int FP, int MODE, int MINB>
+// RING  = 0: inputs loaded in place; 1 / 2: cp.async input ring with fp32 / bf16 G (bf16 tables,
+//         3 channels).  A compile-time choice: with both paths in one function every instruction
+//         after their merge point waited on the scoreboards of EITHER path's loads.
+template <typename T, int FP, int MODE, int MINB, int RING>
 __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const BwdParams p) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
@@ -128,8 +135,13 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
 #pragma unroll
   for (int i = 0; i < 16; ++i) dav[i] = 0.f;
 
-  constexpr bool RING_OK = !K4 && (sizeof(T) == 2);
-  const bool ring = RING_OK && p.ring;
+  static_assert(RING == 0 || (!K4 && sizeof(T) == 2), "the input ring is for bf16 tables, 3 channels");
+  constexpr bool ring = RING != 0;
+  // ring mode: att / sig of a row (2K floats) travel through the ring too -- lane j of the row's
+  // group copies att[j] (j < K) or sig[j - K] (K <= j < 2K) -- instead of being loaded in place,
+  // where they were a dependent DRAM-latency stall per row
+  constexpr bool AS_RING = ring && LANES >= 8;
+  const bool g_bf16 = RING == 2 ? true : RING == 1 ? false : (p.g_bf16 != 0);
   const int64_t stride = (int64_t)gridDim.x * RPB;
   const int64_t base0 = (int64_t)blockIdx.x * RPB;
   const int64_t n_iter = base0 < p.n_rows ? (p.n_rows - base0 + stride - 1) / stride : 0;
@@ -137,7 +149,11 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
   uint32_t ring_u32 = 0;
   auto ring_issue = [&](int64_t r, int slot) {
     const uint32_t d = ring_u32 + slot * kRingStageBytes;
-    if (p.g_bf16) {
+    if (AS_RING) {
+      if (gl < K) bwd_cp_async4(d + kRingAsOff + sub * 32 + gl * 4, p.att + r * K + gl);
+      else if (gl < 2 * K) bwd_cp_async4(d + kRingAsOff + sub * 32 + 16 + (gl - K) * 4, p.sig + r * K + (gl - K));
+    }
+    if (g_bf16) {
       bwd_cp_async16(d + lane * 32, reinterpret_cast<const __nv_bfloat16*>(p.g) + r * p.ldg + f0);
     } else {
       const float* gr = p.g + r * p.ldg + f0;
@@ -164,30 +180,9 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
   // staging tile of the narrow-row peer push
   T* push_stage = (p.peers.n > 0 && LANES < 32) ? reinterpret_cast<T*>(tail) : nullptr;
 
-  // att / sig of a row (2K floats) are prefetched ONE iteration ahead, one float per lane: lane j of
-  // the row's group loads att[j] (j < K) or sig[j - K] (K <= j < 2K), and the values are broadcast
-  // by shuffle where they are used.  Loaded in place they were a dependent DRAM-latency stall per
-  // row that nothing but the other 3 warps of the scheduler could hide.
-  constexpr bool AS_PF = LANES >= 8;
-  float as_nxt = 0.f;
-  auto as_load = [&](const int64_t r) -> float {
-    if (gl < K) return __ldg(p.att + r * K + gl);
-    if (gl < 2 * K) return __ldg(p.sig + r * K + (gl - K));
-    return 0.f;
-  };
-  if (AS_PF && n_iter > 0) {
-    const int64_t r = base0 + warp * RPW + sub;
-    if (r < p.n_rows) as_nxt = as_load(r);
-  }
-
   for (int64_t it = 0; it < n_iter; ++it) {
     const int64_t row = base0 + it * stride + warp * RPW + sub;
     const bool valid = row < p.n_rows;
-    const float as_cur = as_nxt;
-    if (AS_PF) {
-      as_nxt = 0.f;
-      if (it + 1 < n_iter && row + stride < p.n_rows) as_nxt = as_load(row + stride);
-    }
     float G[8], o[KMAX][8], al[KMAX], sg[KMAX];
 #pragma unroll
     for (int t = 0; t < 8; ++t) G[t] = 0.f;
@@ -200,10 +195,17 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
     }
     if (ring) {
       bwd_cp_async_wait<kRingStages - 1>();
+      if (AS_RING) __syncwarp();   // att / sig were copied by other lanes of the group
       const int slot = (int)(it & (kRingStages - 1));
       if (valid) {
         const uint8_t* d = ring_w + slot * kRingStageBytes;
-        if (p.g_bf16) {
+        if (AS_RING) {
+          const float4 a4 = *reinterpret_cast<const float4*>(d + kRingAsOff + sub * 32);
+          const float4 s4 = *reinterpret_cast<const float4*>(d + kRingAsOff + sub * 32 + 16);
+          al[0] = a4.x; al[1] = a4.y; al[2] = a4.z;
+          sg[0] = s4.x; sg[1] = s4.y; sg[2] = s4.z;
+        }
+        if (g_bf16) {
           unpack_bf16x8(*reinterpret_cast<const uint4*>(d + lane * 32), G);
         } else {
           const float4 a = *reinterpret_cast<const float4*>(d + lane * 32);
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
       bwd_cp_async_commit();
     } else if (valid) {
       const float* gr = p.g + row * p.ldg + f0;
-      if (p.g_bf16) {
+      if (g_bf16) {
         const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(p.g) + row * p.ldg + f0;
         if (p.vec_g && f0 + 8 <= p.f) {
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(gb));
@@ -270,19 +272,12 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
         s4.load(reinterpret_cast<const T*>(p.o_s) + row * FP + f0);
         s4.to_float(o[KMAX - 1]);
       }
-      if (!AS_PF) {
+      if (!AS_RING) {
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
           al[k] = __ldg(p.att + row * K + k);
           sg[k] = __ldg(p.sig + row * K + k);
         }
-      }
-    }
-    if (AS_PF) {   // all lanes shuffle (invalid rows carry zeros, as the in-place loads left them)
-#pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        al[k] = __shfl_sync(0xffffffffu, as_cur, sub * LANES + k);
-        sg[k] = __shfl_sync(0xffffffffu, as_cur, sub * LANES + K + k);
       }
     }
     // d_alpha
@@ -464,8 +459,8 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
 static int g_mix_bwd_minb = 2;
 static int g_mix_bwd_ring = 1;
 
-template <typename T, int FP, int MODE, int MINB>
-static int launch_bwd_impl(const BwdParams& p, cudaStream_t st) {
+template <typename T, int FP, int MODE, int MINB, int RING>
+static int launch_bwd_ring(const BwdParams& p, cudaStream_t st) {
   constexpr int LANES = FP / 8;
   constexpr int RPB = (32 / LANES) * kBwdWarps;
   constexpr bool K4 = (MODE & 2) != 0;
@@ -476,18 +471,26 @@ static int launch_bwd_impl(const BwdParams& p, cudaStream_t st) {
   const int64_t cap = 148 * (MINB == 3 ? 6 : 4);
   if (blocks > cap) blocks = cap;
   size_t smem = sizeof(float) * BwdSmem<FP, MODE>::kFloatsPadded;
-  if (!K4 && sizeof(T) == 2 && p.ring) smem += (size_t)kBwdWarps * kRingStages * kRingStageBytes;
+  if (RING) smem += (size_t)kBwdWarps * kRingStages * kRingStageBytes;
   if (p.peers.n > 0 && LANES < 32) smem += (size_t)kBwdWarps * 512 * sizeof(T);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(mix_bwd_kernel<T, FP, MODE, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(mix_bwd_kernel<T, FP, MODE, MINB, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       set_error("mix_bwd: cannot raise dynamic shared memory to %zu: %s", smem, cudaGetErrorString(e));
       return (int)e;
     }
   }
-  mix_bwd_kernel<T, FP, MODE, MINB><<<(unsigned)blocks, kBwdWarps * 32, smem, st>>>(p);
+  mix_bwd_kernel<T, FP, MODE, MINB, RING><<<(unsigned)blocks, kBwdWarps * 32, smem, st>>>(p);
   ACM_LAUNCH_CHECK("mix_bwd");
   return 0;
+}
+
+template <typename T, int FP, int MODE, int MINB>
+static int launch_bwd_impl(const BwdParams& p, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2 && (MODE & 2) == 0) {
+    if (p.ring) return p.g_bf16 ? launch_bwd_ring<T, FP, MODE, MINB, 2>(p, st) : launch_bwd_ring<T, FP, MODE, MINB, 1>(p, st);
+  }
+  return launch_bwd_ring<T, FP, MODE, MINB, 0>(p, st);
 }
 
 template <typename T, int FP>

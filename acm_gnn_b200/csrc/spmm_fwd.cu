@@ -32,6 +32,7 @@ struct FwdParams {
   float* att;
   float* sig;
   LongRows lr;
+  const int32_t* row_order;   // optional: slot -> local row (degree-sorted processing order), or nullptr
 };
 
 constexpr int kFwdWarps = 8;
@@ -213,8 +214,11 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
   const int warp = threadIdx.x >> 5;
   const int sub = lane / LANES;
   const int gl = lane % LANES;
-  const int64_t row = (rb * kFwdWarps + warp) * RPW + sub;
-  const bool valid = row < p.n_rows;
+  const int64_t slot_id = (rb * kFwdWarps + warp) * RPW + sub;
+  const bool valid = slot_id < p.n_rows;
+  // several rows share a warp (RPW > 1): the warp walks max(degree) edges, so the caller may hand
+  // in a processing order that puts rows of equal degree next to each other (acm_b200.h)
+  const int64_t row = (RPW > 1 && valid && p.row_order) ? (int64_t)__ldg(p.row_order + slot_id) : slot_id;
 
   int64_t e = 0, e1 = 0;
   if (valid) {
@@ -579,7 +583,8 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
                                 const void* table, const void* h_i, const void* o_s,
                                 const float* pack, int k_channels, int ln_live, int variant, float out_scale,
                                 void* y, int y_dtype, int64_t ldy, void* o_save, float* att, float* sig,
-                                const int32_t* long_rows, int n_long, const float* long_acc, void* stream) {
+                                const int32_t* long_rows, int n_long, const float* long_acc,
+                                const int32_t* row_order, void* stream) {
   using namespace acm;
   ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_mix_fwd: bad dtype %d", dtype);
   ACM_CHECK_ARG(k_channels == 3 || k_channels == 4, "spmm_mix_fwd: k_channels must be 3 or 4");
@@ -594,6 +599,7 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
   p.variant = variant; p.f = f; p.out_scale = out_scale; p.y = reinterpret_cast<float*>(y); p.ldy = ldy; p.o_save = o_save;
   p.y_bf16 = (y_dtype == ACM_BF16);
   p.att = att; p.sig = sig;
+  p.row_order = row_order;
   p.pre_agg = (rowptr == nullptr);
   ACM_CHECK_ARG(!p.pre_agg || (rowscale == nullptr && n_long == 0), "spmm_mix_fwd: the pre-aggregated mode takes no rowscale / long rows");
   p.lr.rows = n_long > 0 ? long_rows : nullptr; p.lr.acc = long_acc; p.lr.n_long = n_long;

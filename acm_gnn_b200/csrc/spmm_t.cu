@@ -18,14 +18,16 @@ template <typename T, int FP, int HINT>
 __global__ void __launch_bounds__(kTWarps * 32)
 spmm_t_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
               const float* __restrict__ val, const T* __restrict__ table, const T* __restrict__ ptab,
-              T* __restrict__ dh_all, const LongRows lr) {
+              T* __restrict__ dh_all, const LongRows lr, const int32_t* __restrict__ row_order) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
   constexpr int TW = 2 * FP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LANES, gl = lane % LANES;
-  const int64_t row = ((int64_t)blockIdx.x * kTWarps + warp) * RPW + sub;
-  if (row >= n_rows) return;  // no cross-lane traffic in this kernel
+  const int64_t slot_id = ((int64_t)blockIdx.x * kTWarps + warp) * RPW + sub;
+  if (slot_id >= n_rows) return;  // no cross-lane traffic in this kernel
+  // degree-sorted processing order (rows of one warp walk max(degree) edges), see acm_b200.h
+  const int64_t row = (RPW > 1 && row_order) ? (int64_t)__ldg(row_order + slot_id) : slot_id;
   int64_t e = __ldg(rowptr + row);
   const int64_t e1 = __ldg(rowptr + row + 1);
   const T* tab = table + gl * 8;
@@ -357,7 +359,8 @@ extern "C" int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row
 extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
                               const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
                               const void* t_table, const void* p_table, void* dh_all,
-                              const int32_t* long_rows, int n_long, const float* long_acc, void* stream) {
+                              const int32_t* long_rows, int n_long, const float* long_acc,
+                              const int32_t* row_order, void* stream) {
   using namespace acm;
   LongRows lr{n_long > 0 ? long_rows : nullptr, long_acc, n_long};
   ACM_CHECK_ARG(n_long == 0 || (long_rows && long_acc), "spmm_t_bwd: long rows need long_rows and long_acc");
@@ -373,10 +376,10 @@ extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
     if (FP <= 32 && g_narrow_row_hint) {                                                           \
       constexpr int H = FP <= 32 ? 1 : 0;                                                          \
       spmm_t_kernel<TT, FP, H><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                         \
-          n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all, lr); \
+          n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all, lr, row_order); \
     } else {                                                                                       \
       spmm_t_kernel<TT, FP, 0><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                         \
-          n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all, lr); \
+          n_rows, row0, rowptr_t, col_t, val_t, (const TT*)t_table, (const TT*)p_table, (TT*)dh_all, lr, row_order); \
     }                                                                                              \
   })
   if (dtype == ACM_BF16) { ACM_T_LAUNCH(__nv_bfloat16); } else { ACM_T_LAUNCH(float); }

@@ -144,6 +144,12 @@ def _long_pass(csr, transposed, table, fp, halves, cdt, st):
     return rows.data_ptr(), int(rows.numel()), acc.data_ptr(), (rows, acc)
 
 
+def _row_order(csr, transposed, fp):
+    """Degree-sorted processing order for the gather kernels when several rows share a warp
+    (fp <= 64: 4 or more rows per warp); None = natural order."""
+    return csr.row_order(transposed) if fp <= 64 else None
+
+
 def _ptr_array(tensors):
     """HOST array of device pointers (NULL for None) for the `const float* const*` ABI arguments."""
     return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
@@ -293,6 +299,7 @@ class AcmLayerFunction(torch.autograd.Function):
             table, csr = h_lh, (0, 0, 0)      # pre-aggregated: only the epilogue of the fused kernel runs
             row0 = 0
             lr = (0, 0, 0, None)
+            order = None
         else:
             # staging copy of the layer input in the storage dtype (row stride padded to 8)
             if staged is not None:
@@ -335,6 +342,7 @@ class AcmLayerFunction(torch.autograd.Function):
             csr = (op.low.rowptr.data_ptr(), op.low.col.data_ptr(), op.low.val.data_ptr())
             row0 = op.row0
             lr = _long_pass(op.low, False, table, fp, 2, cdt, st)
+            order = _row_order(op.low, False, fp)
 
         o_s = None
         if K == 4:
@@ -364,7 +372,7 @@ class AcmLayerFunction(torch.autograd.Function):
                   table.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s), pack.data_ptr(),
                   K, int(cfg.ln_live), int(cfg.variant), float(cfg.out_scale),
                   y.data_ptr(), _lib.ACM_BF16 if y_bf16 else _lib.ACM_F32, f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig),
-                  lr[0], lr[1], lr[2], st, tag=fp)
+                  lr[0], lr[1], lr[2], _lib.ptr(order), st, tag=fp)
         del lr
         if need_grad and agg_first:
             o_save = h_lh
@@ -431,7 +439,7 @@ class AcmLayerFunction(torch.autograd.Function):
             lr = _long_pass(op.low, True, t_table, fp, 2, cdt, st)
             _lib.call("acm_spmm_t_bwd", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
                       op.low.val_t.data_ptr(), t_table.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(),
-                      lr[0], lr[1], lr[2], st, tag=fp)
+                      lr[0], lr[1], lr[2], _lib.ptr(_row_order(op.low, True, fp)), st, tag=fp)
             del t_table, lr
             _lib.call("acm_gemm_bwd_dw", impl, cdt, xs.data_ptr(), ldx, dh_all.data_ptr(), dwcat.data_ptr(), n, fin, fp, st, tag=fp)
             if ctx.x_needs_grad and ctx.x_dtype == torch.bfloat16 and fin % 8 == 0:

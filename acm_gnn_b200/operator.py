@@ -106,6 +106,30 @@ class CsrMatrix:
         setattr(self, attr, res)
         return res
 
+    # -- narrow rows: processing order that groups rows of equal degree ----------------------------
+    ORDER_WINDOW = 4096
+
+    def row_order(self, transposed=False):
+        """int32 permutation of the local rows: inside every window of ORDER_WINDOW consecutive rows
+        the rows are sorted by their number of stored edges (stable).  The gather kernels put
+        32/(fp/8) rows in one warp and walk max(degree) edges, so neighbours of equal degree remove
+        the divergence (measured on the 10 M-node graph, 16 rows per warp: 65 % of the lanes were
+        active in the gather loop), while the windows keep the streamed per-row accesses local.
+        Built once per operator (``ACMB200_ROW_ORDER=0`` disables it)."""
+        attr = "_order_t" if transposed else "_order"
+        if hasattr(self, attr):
+            return getattr(self, attr)
+        import os
+        res = None
+        if os.environ.get("ACMB200_ROW_ORDER", "1") != "0" and self.n_rows > 1:
+            rowptr = self.rowptr_t if transposed else self.rowptr
+            deg = rowptr[1:] - rowptr[:-1]
+            win = torch.arange(self.n_rows, device=deg.device, dtype=torch.int64) // self.ORDER_WINDOW
+            key = win * (int(deg.max().item()) + 1) + deg
+            res = torch.argsort(key, stable=True).to(torch.int32).contiguous()
+        setattr(self, attr, res)
+        return res
+
     def rows(self):
         return torch.repeat_interleave(torch.arange(self.n_rows, device=self.device, dtype=torch.int64),
                                        self.rowptr[1:] - self.rowptr[:-1])

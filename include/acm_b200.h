@@ -174,13 +174,19 @@ int acm_spmm_long_rows(int dtype, int fp, int halves, int64_t n_seg, const int32
  * y is fp32 (the reference boundary) or, y_dtype = ACM_BF16, bf16 inter-layer activations
  * (the next layer's input cast folded into this epilogue; acm_mix_bwd accepts g in bf16 likewise).
  * rowptr == col == NULL selects the pre-aggregated mode of the aggregate-first order: the
- * own rows of `table` already hold [S_L | S_H] and only the epilogue runs. */
+ * own rows of `table` already hold [S_L | S_H] and only the epilogue runs.
+ * row_order (may be NULL = natural order): a permutation of [0, n_rows) giving the order in which
+ * the rows are PROCESSED.  With narrow rows several rows share a warp (32 / (fp/8) of them) and the
+ * warp walks max(degree) edges; an order that puts rows of equal degree next to each other (sorted
+ * by degree inside windows of a few thousand consecutive rows, so that the streamed accesses stay
+ * local) removes that divergence.  Results do not depend on it.  Ignored for fp >= 256. */
 int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
                      const int64_t* rowptr, const int32_t* col, const float* val, const float* rowscale,
                      const void* table, const void* h_i, const void* o_s,
                      const float* pack, int k_channels, int ln_live, int variant, float out_scale,
                      void* y, int y_dtype, int64_t ldy, void* o_save, float* att, float* sig,
-                     const int32_t* long_rows, int n_long, const float* long_acc, void* stream);
+                     const int32_t* long_rows, int n_long, const float* long_acc,
+                     const int32_t* row_order, void* stream);
 
 /* Register/occupancy trade-off of mix_bwd_kernel (plain 3-channel mode): 2 (default) or 3 resident
  * CTAs per SM. */
@@ -213,11 +219,13 @@ int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
  *   dHL = A_low^T dS_L ; dHH = dS_H - A_low^T dS_H     -> dh_all[:, 0:2fp]
  * (rowptr_t,col_t,val_t) is the CSR of A_low^T (same arrays as A_low when the pattern is
  * symmetric, with acm_csr_transpose_values).  variant 1: p_table = the relu'd forward
- * table; the result is masked by p > 0 (relu before aggregation). */
+ * table; the result is masked by p > 0 (relu before aggregation).  row_order: as in
+ * acm_spmm_mix_fwd, for the rows of A_low^T. */
 int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
                    const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
                    const void* t_table, const void* p_table, void* dh_all,
-                   const int32_t* long_rows, int n_long, const float* long_acc, void* stream);
+                   const int32_t* long_rows, int n_long, const float* long_acc,
+                   const int32_t* row_order, void* stream);
 
 /* Plain single-table aggregation out = [relu](A . table), table T [*, fp]; used for the
  * structure channel relu(mm(adj_low_unnormalized, struc_low)) (layers.py:207-209) and its

@@ -30,7 +30,7 @@ def test_argument_validation_without_gpu():
     """Bad arguments are rejected before any launch, with an error string."""
     from acm_gnn_b200 import _lib
     lib = _lib.load()
-    rc = lib.acm_spmm_mix_fwd(7, 256, 256, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 0, 0, 3.0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
+    rc = lib.acm_spmm_mix_fwd(7, 256, 256, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 0, 0, 3.0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0)
     assert rc == 10001
     assert b"dtype" in lib.acm_last_error_string()
     rc = lib.acm_cast_pad(0, 1, 1, 1, 0, 1, 4, 0)

@@ -179,3 +179,43 @@ def test_narrow_row_hint_bit_identical(f, mode):
     assert torch.isfinite(res[0][0]).all()
     assert torch.equal(res[0][0], res[1][0])
     assert torch.equal(res[0][1], res[1][1])
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("f", [5, 16, 64])
+def test_degree_sorted_row_order_bit_identical(f, mode, monkeypatch):
+    """The gather kernels may process the rows in a degree-sorted order (CsrMatrix.row_order):
+    the per-row accumulation order is unchanged, so outputs and gradients are bitwise equal to the
+    natural order.  Skewed degrees (1 .. > 256: long rows included) and a row count that is not a
+    multiple of the rows per CTA."""
+    import acm_gnn_b200 as A
+    os.environ["ACMB200_DTYPE"] = mode
+    n = 5003
+    g = torch.Generator().manual_seed(11)
+    src = torch.randint(0, n, (60000,), generator=g)
+    dst = (n * torch.rand(60000, generator=g, dtype=torch.float64).pow(3.0)).long().clamp(max=n - 1)
+    row, col = torch.cat([src, dst]).cuda(), torch.cat([dst, src]).cuda()
+    torch.manual_seed(1)
+    layer = A.GraphConvolution(40, f, n, "acmgcn", variant=False).cuda()
+    x0 = torch.rand(n, 40, device="cuda")
+    res = []
+    for on in ("1", "0"):
+        monkeypatch.setenv("ACMB200_ROW_ORDER", on)
+        op = A.AcmOperator.from_edges(row, col, n)          # the order is cached per operator
+        order = op.low.row_order()
+        if on == "1":
+            assert order is not None and torch.equal(torch.sort(order.long()).values, torch.arange(n, device="cuda"))
+            deg = (op.low.rowptr[1:] - op.low.rowptr[:-1])[order.long()]
+            w = op.low.ORDER_WINDOW
+            assert bool((deg[:w][1:] >= deg[:w][:-1]).all()) and int(deg.max()) > 256
+            assert int(order[:w].max()) < w                  # windows keep the rows local
+        else:
+            assert order is None
+        x = x0.clone().requires_grad_(True)
+        layer.zero_grad(set_to_none=True)
+        y = layer(x, op, None, None)
+        y.square().sum().backward()
+        res.append((y.detach().clone(), x.grad.detach().clone(), layer.att_low.detach().clone()))
+    assert torch.isfinite(res[0][0]).all()
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)

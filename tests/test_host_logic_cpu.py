@@ -141,3 +141,25 @@ def test_graphed_step_has_no_cpu_path():
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         GraphedTrainStep(model, opt, x, (None, None, None), torch.zeros(10, dtype=torch.int64), torch.ones(10, dtype=torch.uint8))
+
+
+def test_row_order_groups_equal_degrees_inside_windows():
+    """CsrMatrix.row_order: a permutation, degree-sorted (stable) inside each window of consecutive rows."""
+    from acm_gnn_b200.operator import CsrMatrix
+    g = torch.Generator().manual_seed(0)
+    n = 10000
+    deg = torch.randint(0, 40, (n,), generator=g)
+    rowptr = torch.zeros(n + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(deg, 0)
+    m = CsrMatrix(n, n, rowptr, torch.zeros(int(rowptr[-1]), dtype=torch.int32), torch.zeros(int(rowptr[-1])))
+    order = m.row_order().long()
+    assert torch.equal(torch.sort(order).values, torch.arange(n))
+    w = m.ORDER_WINDOW
+    for s in range(0, n, w):
+        blk = order[s:s + w]
+        assert int(blk.min()) >= s and int(blk.max()) < min(n, s + w)
+        d = deg[blk]
+        assert bool((d[1:] >= d[:-1]).all())
+        same = d[1:] == d[:-1]
+        assert bool((blk[1:][same] > blk[:-1][same]).all())      # stable: ties keep the natural order
+    assert m.row_order() is m.row_order()                        # cached
