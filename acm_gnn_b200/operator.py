@@ -113,15 +113,18 @@ class CsrMatrix:
         """int32 permutation of the local rows: inside every window of ORDER_WINDOW consecutive rows
         the rows are sorted by their number of stored edges (stable).  The gather kernels put
         32/(fp/8) rows in one warp and walk max(degree) edges, so neighbours of equal degree remove
-        the divergence (measured on the 10 M-node graph, 16 rows per warp: 65 % of the lanes were
+        the divergence (on the 10 M-node uniform graph, 16 rows per warp, 65 % of the lanes are
         active in the gather loop), while the windows keep the streamed per-row accesses local.
-        Built once per operator (``ACMB200_ROW_ORDER=0`` disables it)."""
+        OPT-IN (``ACMB200_ROW_ORDER=1``): measured on that graph it does not pay -- 4.63 vs 4.55 ms
+        forward, 4.88 vs 4.87 ms backward -- because those kernels are bound by the rate of random
+        64-byte DRAM accesses (4.1 TB/s), not by lane utilisation; kept for strongly skewed graphs.
+        Built once per operator."""
         attr = "_order_t" if transposed else "_order"
         if hasattr(self, attr):
             return getattr(self, attr)
         import os
         res = None
-        if os.environ.get("ACMB200_ROW_ORDER", "1") != "0" and self.n_rows > 1:
+        if os.environ.get("ACMB200_ROW_ORDER", "0") == "1" and self.n_rows > 1:
             rowptr = self.rowptr_t if transposed else self.rowptr
             deg = rowptr[1:] - rowptr[:-1]
             win = torch.arange(self.n_rows, device=deg.device, dtype=torch.int64) // self.ORDER_WINDOW

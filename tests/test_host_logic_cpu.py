@@ -143,9 +143,10 @@ def test_graphed_step_has_no_cpu_path():
         GraphedTrainStep(model, opt, x, (None, None, None), torch.zeros(10, dtype=torch.int64), torch.ones(10, dtype=torch.uint8))
 
 
-def test_row_order_groups_equal_degrees_inside_windows():
+def test_row_order_groups_equal_degrees_inside_windows(monkeypatch):
     """CsrMatrix.row_order: a permutation, degree-sorted (stable) inside each window of consecutive rows."""
     from acm_gnn_b200.operator import CsrMatrix
+    monkeypatch.setenv("ACMB200_ROW_ORDER", "1")
     g = torch.Generator().manual_seed(0)
     n = 10000
     deg = torch.randint(0, 40, (n,), generator=g)
