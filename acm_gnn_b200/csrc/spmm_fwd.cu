@@ -96,6 +96,12 @@ __device__ __forceinline__ void fwd_epilogue(const FwdParams& p, const int64_t r
   constexpr int KMAX = (MODE & 2) ? 4 : 3;
   constexpr int K = KMAX;
   constexpr int TW = 2 * FP;
+  // bf16 storage mode: the six exponentials and three reciprocals of the per-row attention are a
+  // fifth of this (issue-bound) epilogue's instructions; the approximate forms (ex2.approx /
+  // rcp.approx, ~2 ulp) are far below the bf16 rounding of the tables they are applied to.  The
+  // fp32 parity mode keeps the IEEE forms.  The backward reads the saved att / sig, so forward and
+  // backward stay consistent either way.
+  constexpr bool FAST = sizeof(T) == 2;
   float z[KMAX];
   constexpr bool ln = LN;
   const float inv_f = 1.f / (float)p.f;
@@ -123,12 +129,12 @@ __device__ __forceinline__ void fwd_epilogue(const FwdParams& p, const int64_t r
       }
       const float var = group_sum<LANES>(s2) * inv_f;
       dot = group_sum<LANES>(dot);
-      z[k] = dot / sqrtf(var + kLnEps) + s_sc[k];
+      z[k] = (FAST ? dot * rsqrtf(var + kLnEps) : dot / sqrtf(var + kLnEps)) + s_sc[k];
     }
   }
   float s[KMAX], a[KMAX];
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k) s[k] = sigmoidf_acc(z[k]);
+  for (int k = 0; k < KMAX; ++k) s[k] = FAST ? __fdividef(1.f, 1.f + __expf(-z[k])) : sigmoidf_acc(z[k]);
   float mx = -INFINITY;
   const float inv_k = 1.f / (float)K;
 #pragma unroll
@@ -143,10 +149,10 @@ __device__ __forceinline__ void fwd_epilogue(const FwdParams& p, const int64_t r
   float den = 0.f;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
-    a[k] = (k < K) ? expf(a[k] - mx) : 0.f;
+    a[k] = (k < K) ? (FAST ? __expf(a[k] - mx) : expf(a[k] - mx)) : 0.f;
     den += a[k];
   }
-  const float rden = 1.f / den;
+  const float rden = FAST ? __fdividef(1.f, den) : 1.f / den;
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) a[k] *= rden;
 
