@@ -130,6 +130,22 @@ struct Slice8<float> {
   __device__ __forceinline__ void zero() { a = make_float4(0, 0, 0, 0); b = a; }
 };
 
+// ---- cp.async (LDGSTS): global -> shared without register staging ---------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// one 8-feature slice (16 B in bf16, 32 B in fp32)
+template <typename T> __device__ __forceinline__ void cp_async_slice(uint32_t dst, const T* src) {
+  cp_async16(dst, src);
+  if (sizeof(T) == 4) cp_async16(dst + 16, reinterpret_cast<const char*>(src) + 16);
+}
+
+extern int g_gather_mode;       // spmm_fwd.cu; set by acm_set_gather_mode
+
 // reduce over the LANES lanes of one row group (LANES is a power of two <= 32; groups are
 // aligned, so xor-shuffles stay inside the group)
 template <int LANES>

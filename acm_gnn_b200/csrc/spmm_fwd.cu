@@ -46,18 +46,6 @@ constexpr int kUnroll = 4;
 // in flight).  A lane only ever reads back the bytes it copied itself: no warp synchronisation.
 template <typename T> struct AsyncCfg { static constexpr int kStages = sizeof(T) == 2 ? 8 : 4; };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-template <typename T> __device__ __forceinline__ void cp_async_slice(uint32_t dst, const T* src) {
-  cp_async16(dst, src);
-  if (sizeof(T) == 4) cp_async16(dst + 16, reinterpret_cast<const char*>(src) + 16);
-}
-
 // ---- bulk-copy gather (gather mode 2, FP = 256 only: one row per warp) -------------------------
 // The neighbour's whole [HL|HH] table row (1 KB in bf16) is one contiguous span, so ONE
 // cp.async.bulk (the TMA engine's linear-copy form, SASS UBLKCP) issued by lane 0 replaces the
@@ -522,7 +510,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, GM == 4 ? 3 : 1) spmm_mix_fwd_
   }
 }
 
-static int g_gather_mode = 1;  // 0: LDG register staging, 1: cp.async ring, 2: cp.async.bulk ring (FP = 256)
+int g_gather_mode = 1;  // 0: LDG register staging, 1: cp.async ring, 2: cp.async.bulk ring (FP = 256)
 
 template <typename K>
 static int raise_smem(K kernel, size_t smem) {

@@ -1,0 +1,51 @@
+"""bench.py contract on the GPU arm, at a size that runs in seconds: ONE JSON line with the agreed
+keys, a live roofline of the dominant kernel, an end-to-end leg that starts from host buffers, a
+CPU baseline timed beside it, and a non-zero count of library launches."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from helpers import ROOT
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["--nodes", "20000", "--edges", "400000", "--fin", "64", "--hidden", "64", "--nclass", "8",
+         "--steps", "3", "--warmup", "3", "--cpu-nodes", "2000"]
+
+
+def _bench(*extra):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *SMALL, *extra], cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    return json.loads(lines[0])
+
+
+def test_bench_default_arm_contract():
+    d = _bench()
+    assert d["metric"] == "acm_gcn_train_step_edges_per_sec" and d["unit"] == "edges/s"
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["dtype"] == "bf16"
+    assert d["gpu_launches"] >= 3 * 10                      # >= 10 library launches per step
+    roof = d["roofline"]
+    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["achieved"] > 0
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9 and roof["launches_timed"] == 3
+    e2e = d["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 20000 * 64 * 4 + 20000 * 8 and e2e["d2h_bytes_per_step"] == 4
+    cpu = d["cpu_baseline"]
+    assert cpu["value"] > 0 and cpu["kind"] in ("reference", "port") and cpu["cores"] == os.cpu_count()
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert "workload" in d["config"] and d["loss"] == d["loss"]
+    assert any(k.startswith("acm_spmm_agg_first") for k in d["kernel_ms_per_step"])
+    assert d["north_star_order"]["roofline"]["achieved"] > 0
+
+
+def test_bench_graph_mode_contract():
+    d = _bench("--graph", "--no-cpu-baseline")
+    assert d["cuda_graph"] is True and d["eager_ms_per_step"] > 0 and d["ms_per_step"] > 0
+    assert d["gpu_launches"] >= 3 * 10 and d["roofline"] is None
+    assert d["e2e"]["value"] > 0 and d["loss"] == d["loss"]
