@@ -9,4 +9,4 @@ from .models import GCN  # noqa: F401
 from .operator import AcmOperator, CsrMatrix, cached_operator  # noqa: F401
 from .graphed import GraphedForward, GraphedTrainStep  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.1.1"
