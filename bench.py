@@ -164,7 +164,9 @@ def cpu_step_factory(n, e_directed, fin, hidden, nclass):
     """One CPU train step of the 2-layer acmgcn on a synthetic graph, as ``train_model`` does it
     (ACM-Pytorch/utils.py:547-574: zero_grad, forward, log_softmax + nll_loss on the train rows,
     backward, Adam.step), with both operators as sparse COO (the torch.sparse.mm path
-    BASELINE.json names; ACM-Geometric/train.py:77-80).  Returns (step, nnz, kind):
+    BASELINE.json names; ACM-Geometric/train.py:77-80).  Returns (step, nnz, kind, csr_adj) where
+    ``step(adj=None)`` runs one train step (on other operator tensors when ``adj`` is given) and
+    ``csr_adj()`` builds the sparse-CSR form of the operators (None for the oracle port):
     kind "reference" = the reference's own GCN module (models/models.py, layers.py) imported
     unmodified from baseline/_ref; kind "port" = oracle/acm_oracle.py when it is not staged."""
     import torch
@@ -200,8 +202,7 @@ def cpu_step_factory(n, e_directed, fin, hidden, nclass):
 
         # informational second point: the same reference module fed CSR operators (MKL path) instead
         # of the COO tensors its own drivers build -- a stronger CPU baseline than the stock path
-        ref_step.csr_adj = lambda: (low.to_sparse_csr(), high.to_sparse_csr())
-        return ref_step, op.nnz, "reference"
+        return ref_step, op.nnz, "reference", (lambda: (low.to_sparse_csr(), high.to_sparse_csr()))
     gp = torch.Generator().manual_seed(42)
     params = O.init_gcn_params(fin, hidden, nclass, 0, "acmgcn", 0, gp)
     leaves = [t.requires_grad_(True) for grp in params.values() for k, t in grp.items() if not k.startswith(("layer_norm", "struc", "att_struc"))]
@@ -215,12 +216,12 @@ def cpu_step_factory(n, e_directed, fin, hidden, nclass):
         opt.step()
         return float(loss.detach())
 
-    return step, op.nnz, "port"
+    return step, op.nnz, "port", None
 
 
 def time_cpu(steps, warmup, n, args):
     e = int(round(args.edges * (n / args.nodes)))
-    step, nnz, kind = cpu_step_factory(n, e, args.fin, args.hidden, args.nclass)
+    step, nnz, kind, csr_adj = cpu_step_factory(n, e, args.fin, args.hidden, args.nclass)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -228,12 +229,12 @@ def time_cpu(steps, warmup, n, args):
         step()
     dt = (time.perf_counter() - t0) / steps
     csr = None
-    if hasattr(step, "csr_adj"):
+    if csr_adj is not None:
         try:
             import warnings
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
-                adj = step.csr_adj()
+                adj = csr_adj()
                 step(adj)
                 t1 = time.perf_counter()
                 for _ in range(2):
@@ -243,8 +244,7 @@ def time_cpu(steps, warmup, n, args):
                    "note": "same reference module, operators converted to sparse CSR (not the reference's stock COO path); 1 warm-up + 2 steps"}
         except Exception as e:
             csr = {"error": repr(e)}
-    time_cpu.csr = csr
-    return nnz / dt, dt * 1e3, nnz, kind
+    return nnz / dt, dt * 1e3, nnz, kind, csr
 
 
 def run_reference(args):
@@ -255,7 +255,7 @@ def run_reference(args):
     # cuda:0 whenever one is visible, models/layers.py:10-11)
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
     n = min(args.cpu_nodes, args.nodes)
-    val, ms, nnz, kind = time_cpu(args.steps, args.warmup, n, args)
+    val, ms, nnz, kind, csr = time_cpu(args.steps, args.warmup, n, args)
     sample = (("the reference's own GCN module (baseline/_ref/ACM-Pytorch/models, unmodified)" if kind == "reference"
                else "CPU oracle port (oracle/acm_oracle.py)")
               + f", torch.sparse.mm COO operators, fp32, full train step on a scaled graph N={n}, nnz={nnz} "
@@ -266,7 +266,7 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": sample,
-                         "csr_variant": getattr(time_cpu, "csr", None)},
+                         "csr_variant": csr},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
