@@ -18,7 +18,10 @@ nll_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int c, const int6
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   float li = 0.f;
   if (i < n) {
-    const bool on = mask ? (mask[i] != 0) : true;
+    // a row whose label is outside [0, c) (e.g. the -1 of unlabeled nodes) is treated as unselected:
+    // torch's nll_loss would raise; reading x[label] out of bounds is never an option
+    const int64_t lab64 = labels[i];
+    const bool on = (mask ? (mask[i] != 0) : true) && lab64 >= 0 && lab64 < c;
     float v[CMAX];
     const float* xr = x + i * ld;
     if (on) {
@@ -45,7 +48,7 @@ nll_kernel(const float* __restrict__ x, int64_t ld, int64_t n, int c, const int6
         v[j] = (j < c) ? expf(v[j] - mx) : 0.f;
         s += v[j];
       }
-      const int lab = (int)labels[i];
+      const int lab = (int)lab64;
       const float xl = __ldg(xr + lab);  // L1 hit
       li = (logf(s) + mx - xl) * scale;
       if (dx) {

@@ -65,10 +65,16 @@ class LayerConfig:
         return _lib.GEMM_TCGEN05 if g == "tcgen05" else _lib.GEMM_SIMT
 
 
+_TC_OK = None
+
+
 def tc_available() -> bool:
-    """The tcgen05 GEMM kernels (gemm_tc.cu) are the default for bf16 storage; set
-    ACMB200_GEMM=simt to force the CUDA-core path."""
-    return True
+    """tcgen05 GEMM kernels (gemm_tc.cu) need an sm_100 device (the library is built for sm_100a
+    only) -- they are the default for bf16 storage there; ACMB200_GEMM=simt forces the CUDA-core path."""
+    global _TC_OK
+    if _TC_OK is None:
+        _TC_OK = torch.cuda.is_available() and torch.cuda.get_device_capability()[0] == 10
+    return _TC_OK
 
 
 def reorder_enabled(cfg: LayerConfig) -> bool:
@@ -93,8 +99,45 @@ def use_aggregate_first(cfg: LayerConfig, fin: int, fp: int, x_needs_grad: bool)
     return padded_width(fin) <= 2 * fp
 
 
+def _knob(name: str, default: str = "auto") -> bool:
+    v = os.environ.get(name, default).lower()
+    if v in ("auto", "1", "on"):
+        return True
+    if v in ("off", "0"):
+        return False
+    raise ValueError(f"{name}={v!r}: expected auto or off")
+
+
+def use_input_backward(cfg: LayerConfig, fin: int, fp: int, x_needs_grad: bool) -> bool:
+    """Transform-first variant-0 layer whose input needs no gradient: the transposed aggregation
+    only feeds the weight gradients, dW_L = X^T (A^T dS_L) = (A X)^T dS_L and
+    dW_H = X^T (dS_H - A^T dS_H) = (X - A X)^T dS_H, so the backward aggregates the layer INPUT
+    (Fin wide, recomputed every step -- nothing is cached across steps) instead of gathering the
+    2*out_features wide [dS_L|dS_H] table.  Under a row partition the input rows of all ranks are
+    already resident (StagedInput) or narrower to all-gather than the table, so the backward of
+    such a layer needs NO exchange at all.  ``ACMB200_BWD_INPUT=off`` keeps the transposed
+    aggregation of the reference's autograd order."""
+    if cfg.variant or x_needs_grad or fin > 256 or not _knob("ACMB200_BWD_INPUT"):
+        return False
+    return padded_width(fin) <= 2 * fp
+
+
+def use_local_table(cfg: LayerConfig, ldx: int, fp: int) -> bool:
+    """Row partition, transform-first order (SURVEY 7 "what to all-gather"): exchange the NARROWER
+    of {layer input X, [HL|HH] table}.  When the input row is not wider than the table row every
+    rank builds the whole [HL|HH] table itself from the all-gathered input (one redundant tcgen05
+    GEMM, ~3 ms at the headline size) instead of receiving (P-1)/P of a 2*out_features wide table
+    over NVLink (10.24 GB per step at the headline size).  ``ACMB200_LOCAL_TABLE=off`` keeps the
+    fused push / NCCL all-gather of the table."""
+    return cfg.dist is not None and ldx <= 2 * fp and _knob("ACMB200_LOCAL_TABLE")
+
+
 def default_dtype() -> str:
-    d = os.environ.get("ACMB200_DTYPE", "bf16").lower()
+    """Storage of the feature tables behind the reference-facing modules.  The reference computes in
+    fp32, so an unmodified train.py launched through run.py gets fp32 tables (the mode held to the
+    2e-5 parity tolerance) unless the user opts in to bf16 storage with ACMB200_DTYPE=bf16 (what
+    BASELINE configs 2-5 name, and what bench.py passes explicitly)."""
+    d = os.environ.get("ACMB200_DTYPE", "fp32").lower()
     if d in ("bf16", "bfloat16"):
         return "bf16"
     if d in ("fp32", "f32", "float32"):
@@ -182,6 +225,31 @@ def pack_params(cfg, fp, f, fin, ldt, ws, a_vecs, att_vec, ln_params, need_wt, s
     return wcat, wcat_t, pack
 
 
+def _stage_rows(x, tdt, cdt, ldx, st):
+    """Copy of the layer input in the storage dtype with row stride ``ldx`` (zero padded)."""
+    n, fin = x.shape
+    xc = x.detach().contiguous()
+    if xc.dtype == tdt and ldx == fin:
+        return xc
+    if xc.dtype != torch.float32:
+        xs = torch.zeros(n, ldx, dtype=tdt, device=x.device)
+        xs[:, :fin] = xc
+        return xs
+    xs = torch.empty(n, ldx, dtype=tdt, device=x.device)
+    _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, xs.data_ptr(), cdt, ldx, st)
+    return xs
+
+
+def _aggregate_input(op, x_all, n, ldx, tdt, cdt, st):
+    """Z = A_low X and D = X - Z for the own rows (one gather of the INPUT row per stored edge)."""
+    z = torch.empty(n, ldx, dtype=tdt, device=x_all.device)
+    d = torch.empty(n, ldx, dtype=tdt, device=x_all.device)
+    lr = _long_pass(op.low, False, x_all, ldx, 1, cdt, st)
+    _lib.call("acm_spmm_agg_first", cdt, ldx, n, op.row0, op.low.rowptr.data_ptr(), op.low.col.data_ptr(),
+              op.low.val.data_ptr(), x_all.data_ptr(), z.data_ptr(), d.data_ptr(), lr[0], lr[1], lr[2], st, tag=ldx)
+    return z, d
+
+
 class StagedInput:
     """Layer-0 input features already resident in HBM in the layout the kernels consume: the
     storage-dtype copy padded to the power-of-two width (``xs`` [n_local, ldx]) and, under a row
@@ -193,11 +261,28 @@ class StagedInput:
     the per-step cast and -- multi-GPU -- the per-step all-gather of static input data.  A plain
     fp32 tensor is always accepted too (reference API; staged on every call)."""
 
-    def __init__(self, x, xs, x_all, dtype):
-        self.x, self.xs, self.x_all, self.dtype = x, xs, x_all, dtype
+    def __init__(self, x, xs, x_all, dtype, dist=None):
+        self.x, self.xs, self.x_all, self.dtype, self.dist = x, xs, x_all, dtype, dist
         self.shape = x.shape
         self.device = x.device
         self.is_cuda = x.is_cuda
+
+    def update_(self, x_new: torch.Tensor) -> "StagedInput":
+        """New feature values INTO THE SAME BUFFERS (the only supported way to change a staged input:
+        captured CUDA graphs and saved pointers keep reading ``xs`` / ``x_all``).  Re-runs the cast/pad
+        and, under a row partition, the all-gather."""
+        if x_new.shape != self.x.shape:
+            raise ValueError(f"update_: expected shape {tuple(self.x.shape)}, got {tuple(x_new.shape)}")
+        if self.x.data_ptr() != x_new.data_ptr():
+            self.x.copy_(x_new)
+        n, fin = self.x.shape
+        if self.xs.data_ptr() != self.x.data_ptr():
+            cdt = _lib.ACM_BF16 if self.dtype == "bf16" else _lib.ACM_F32
+            xc = self.x.detach().contiguous()
+            _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, self.xs.data_ptr(), cdt, self.xs.shape[1], _stream())
+        if self.dist is not None:
+            self.x_all.copy_(self.dist.all_gather_rows(self.xs))
+        return self
 
 
 def stage_input(x: torch.Tensor, dtype: Optional[str] = None, dist=None) -> StagedInput:
@@ -216,7 +301,7 @@ def stage_input(x: torch.Tensor, dtype: Optional[str] = None, dist=None) -> Stag
         xs = torch.empty(n, ldx, dtype=tdt, device=x.device)
         _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, xs.data_ptr(), cdt, ldx, _stream())
     x_all = xs if dist is None else dist.all_gather_rows(xs)
-    return StagedInput(x, xs, x_all, dtype)
+    return StagedInput(x, xs, x_all, dtype, dist)
 
 
 class AcmLayerFunction(torch.autograd.Function):
@@ -249,41 +334,37 @@ class AcmLayerFunction(torch.autograd.Function):
         if cfg.ln_live:
             ln_params = [(ln_flat[2 * k], ln_flat[2 * k + 1]) for k in range(K)]
         impl = cfg.gemm_impl(fin)
-        agg_first = use_aggregate_first(cfg, fin, fp, bool(ctx.needs_input_grad[2]))
+        x_needs_grad = bool(ctx.needs_input_grad[2])
+        agg_first = use_aggregate_first(cfg, fin, fp, x_needs_grad)
+        bwd_input = (not agg_first) and use_input_backward(cfg, fin, fp, x_needs_grad)
         # row stride of the staged input = K extent of the transposed weights
-        if agg_first:
-            ldt = padded_width(fin)
+        if agg_first or bwd_input:
+            ldx = padded_width(fin)          # the input-row gather wants a power-of-two table width
         elif staged is not None:
-            ldt = staged.xs.shape[1]
+            ldx = staged.xs.shape[1]
         else:
-            ldt = (fin + 7) // 8 * 8 if cfg.dtype == "bf16" else fin
-        wcat, wcat_t_all, pack = pack_params(cfg, fp, f, fin, ldt, (w_low, w_high, w_mlp), a_vecs, att_vec, ln_params,
+            ldx = (fin + 7) // 8 * 8 if cfg.dtype == "bf16" else fin
+        wcat, wcat_t_all, pack = pack_params(cfg, fp, f, fin, ldx, (w_low, w_high, w_mlp), a_vecs, att_vec, ln_params,
                                              impl == _lib.GEMM_TCGEN05, st)
+        # staging copy of the layer input in the storage dtype, [n, ldx]; under a row partition x_all
+        # holds the rows of every rank (resident in a StagedInput, all-gathered on demand otherwise)
+        if staged is not None:
+            if staged.xs.shape[1] != ldx:
+                raise ValueError("StagedInput was staged for a different layer width")
+            xs, x_all = staged.xs, staged.x_all
+        else:
+            if x.dtype == torch.bfloat16 and cfg.dtype != "bf16":
+                raise ValueError("bf16 input needs ACMB200_DTYPE=bf16")
+            xs, x_all = _stage_rows(x, tdt, cdt, ldx, st), None
         h_i = torch.empty(n, fp, dtype=tdt, device=dev)
         z = d = wcat_t = h_lh = None
         if agg_first:
             h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
             # ---- aggregate-first: Z = A X, D = X - Z, then [S_L|S_H|HI] = [Z W_L | D W_H | X W_I] ----
-            ldx = padded_width(fin)
-            if staged is not None:
-                xs, x_all = staged.xs, staged.x_all
-            else:
-                xc = x.detach().contiguous()
-                if xc.dtype == tdt and ldx == fin:
-                    xs = xc
-                elif xc.dtype != torch.float32:
-                    xs = torch.zeros(n, ldx, dtype=tdt, device=dev)
-                    xs[:, :fin] = xc
-                else:
-                    xs = torch.empty(n, ldx, dtype=tdt, device=dev)
-                    _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, xs.data_ptr(), cdt, ldx, st)
+            if x_all is None:
                 x_all = xs if cfg.dist is None else cfg.dist.all_gather_rows(xs)
-            z = torch.empty(n, ldx, dtype=tdt, device=dev)
-            d = torch.empty(n, ldx, dtype=tdt, device=dev)
-            lr = _long_pass(op.low, False, x_all, ldx, 1, cdt, st)
-            _lib.call("acm_spmm_agg_first", cdt, ldx, n, op.row0, op.low.rowptr.data_ptr(), op.low.col.data_ptr(),
-                      op.low.val.data_ptr(), x_all.data_ptr(), z.data_ptr(), d.data_ptr(), lr[0], lr[1], lr[2], st, tag=ldx)
-            del x_all, lr
+            z, d = _aggregate_input(op, x_all, n, ldx, tdt, cdt, st)
+            x_all = None
             if ldx == fin:
                 wp = wcat
             else:
@@ -301,31 +382,23 @@ class AcmLayerFunction(torch.autograd.Function):
             lr = (0, 0, 0, None)
             order = None
         else:
-            # staging copy of the layer input in the storage dtype (row stride padded to 8)
-            if staged is not None:
-                xs, ldx = staged.xs, staged.xs.shape[1]
-            elif x.dtype == torch.bfloat16:
-                # bf16 activations from the previous ACM layer: already in the storage dtype
-                if cfg.dtype != "bf16":
-                    raise ValueError("bf16 input needs ACMB200_DTYPE=bf16")
-                ldx = (fin + 7) // 8 * 8
-                xc = x.detach().contiguous()
-                if ldx == fin:
-                    xs = xc
-                else:
-                    xs = torch.zeros(n, ldx, dtype=tdt, device=dev)
-                    xs[:, :fin] = xc
-            elif cfg.dtype == "bf16":
-                ldx = (fin + 7) // 8 * 8
-                xs = torch.empty(n, ldx, dtype=tdt, device=dev)
-                xc = x.detach().contiguous()
-                _lib.call("acm_cast_pad", xc.data_ptr(), n, fin, fin, xs.data_ptr(), cdt, ldx, st)
-            else:
-                xs = x.detach().contiguous()
-                ldx = fin
             wcat_t = wcat_t_all
-            push = cfg.dist is not None and impl == _lib.GEMM_TCGEN05 and cfg.dist.push_enabled()
-            if push:
+            local_tab = use_local_table(cfg, ldx, fp)
+            push = (cfg.dist is not None and not local_tab and impl == _lib.GEMM_TCGEN05 and cfg.dist.push_enabled())
+            if local_tab:
+                # exchange the narrower operand: every rank builds the WHOLE [HL|HH] table from the
+                # input rows of all ranks (redundant GEMM) -- no table crosses NVLink
+                if x_all is None:
+                    x_all = cfg.dist.all_gather_rows(xs)
+                table = torch.empty(x_all.shape[0], 2 * fp, dtype=tdt, device=dev)
+                _lib.call("acm_gemm_ab", impl, cdt, x_all.data_ptr(), ldx, wcat.data_ptr(), 3 * fp,
+                          _lib.ptr(wcat_t), ldx, table.data_ptr(), 2 * fp, x_all.shape[0], 2 * fp, fin,
+                          int(cfg.variant), st, tag=f"table{fp}")
+                _lib.call("acm_gemm_ab", impl, cdt, xs.data_ptr(), ldx, wcat[:, 2 * fp:].data_ptr(), 3 * fp,
+                          0 if wcat_t is None else wcat_t[2 * fp:].data_ptr(), ldx, h_i.data_ptr(), fp, n, fp, fin,
+                          0, st, tag=fp)
+                h_lh = table[op.row0:op.row0 + n]
+            elif push:
                 # fused GEMM + all-gather: the epilogue stores every finished [HL|HH] row into all
                 # ranks' tables through NVLink peer mappings; one device-side barrier afterwards
                 # (tables alternate between two buffers, see RowPartition.symm_table)
@@ -339,6 +412,11 @@ class AcmLayerFunction(torch.autograd.Function):
                 _lib.call("acm_gemm_xw_fwd", impl, cdt, xs.data_ptr(), ldx, wcat.data_ptr(), _lib.ptr(wcat_t),
                           h_lh.data_ptr(), h_i.data_ptr(), n, fin, fp, int(cfg.variant), st, tag=fp)
                 table = h_lh if cfg.dist is None else cfg.dist.all_gather_rows(h_lh)
+            if bwd_input:
+                if x_all is None:   # the backward aggregates the input rows of every rank
+                    x_all = xs if cfg.dist is None else cfg.dist.all_gather_rows(xs)
+            else:
+                x_all = None
             csr = (op.low.rowptr.data_ptr(), op.low.col.data_ptr(), op.low.val.data_ptr())
             row0 = op.row0
             lr = _long_pass(op.low, False, table, fp, 2, cdt, st)
@@ -382,8 +460,10 @@ class AcmLayerFunction(torch.autograd.Function):
             ctx.op, ctx.cfg = op, cfg
             ctx.dims = (n, fin, f, fp, K, ldx, impl)
             ctx.agg_first = agg_first
+            ctx.bwd_input = bwd_input
+            ctx.x_all = x_all if bwd_input else None     # resident (staged) or all-gathered input rows
             ctx.x_dtype = x.dtype
-            ctx.x_needs_grad = bool(ctx.needs_input_grad[2])
+            ctx.x_needs_grad = x_needs_grad
             ctx.n_ln = len(ln_flat)
             ctx.struc_rows = 0 if struc_low is None else struc_low.shape[0]
             # variant 1 needs the relu'd forward table (its positivity is the relu mask)
@@ -407,7 +487,7 @@ class AcmLayerFunction(torch.autograd.Function):
         dh_all = torch.empty(n, 3 * fp, dtype=tdt, device=dev)
         dos_pre = torch.empty(n, fp, dtype=tdt, device=dev) if K == 4 else None
         dpack = torch.zeros(12 * fp + 16, dtype=torch.float32, device=dev)
-        push = (cfg.dist is not None and not ctx.agg_first and cfg.dist.push_enabled())
+        push = (cfg.dist is not None and not ctx.agg_first and not ctx.bwd_input and cfg.dist.push_enabled())
         if push:
             # fused mix_bwd + all-gather of the backward operand table (peer stores over NVLink)
             t_table, hdl, ptrs, mc = cfg.dist.symm_table((cfg.layer_key, "bwd"), 2 * fp, tdt, dev)
@@ -426,7 +506,12 @@ class AcmLayerFunction(torch.autograd.Function):
 
         dwcat = torch.zeros(fin, 3 * fp, dtype=torch.float32, device=dev)
         dx = None
-        if ctx.agg_first:
+        if ctx.bwd_input:
+            # transform-first forward, input without gradient: aggregate the input rows here instead of
+            # gathering the [dS_L|dS_H] table (use_input_backward) -- no exchange under a partition
+            z, d = _aggregate_input(op, ctx.x_all, n, ldx, tdt, cdt, st)
+            ctx.x_all = None
+        if ctx.agg_first or ctx.bwd_input:
             # dW_L = (AX)^T dS_L ; dW_H = (X - AX)^T dS_H ; dW_I = X^T dHI -- no transposed aggregation
             for k, (a_op, b_ptr, ldb) in enumerate(((z, t_lh.data_ptr(), 2 * fp),
                                                     (d, t_lh[:, fp:].data_ptr(), 2 * fp),
@@ -530,11 +615,28 @@ class MaskedNllLogSoftmax(torch.autograd.Function):
 
 def nll_log_softmax(out, labels, train_mask=None, n_train=None):
     """Mean NLL of log_softmax(out) over the rows selected by ``train_mask`` (uint8/bool [N]).
-    ``n_train`` overrides the normaliser (global count under a row partition)."""
-    if labels.dtype != torch.int64:
-        labels = labels.to(torch.int64)
-    if train_mask is not None and train_mask.dtype != torch.uint8:
-        train_mask = train_mask.to(torch.uint8)
+    ``n_train`` overrides the normaliser (global count under a row partition).  The fused kernel
+    takes fp32 CUDA logits with at most 64 classes; anything else goes through the reference's own
+    torch glue (F.log_softmax + F.nll_loss, utils.py:567-568) -- same math, not a CPU fallback of
+    the ACM layer.  Labels of the selected rows must lie in [0, C) (the kernel ignores rows whose
+    label is out of range instead of reading out of bounds)."""
+    if not out.is_cuda:
+        raise RuntimeError("acm_gnn_b200: CUDA tensors only (there is no CPU fallback)")
+    if out.dim() != 2:
+        raise ValueError("nll_log_softmax: logits must be [N, C]")
+    labels = labels.to(device=out.device, dtype=torch.int64).contiguous()
+    if labels.shape[0] != out.shape[0]:
+        raise ValueError("nll_log_softmax: labels must have one entry per row of the logits")
+    if train_mask is not None:
+        train_mask = train_mask.to(device=out.device, dtype=torch.uint8).contiguous()
+        if train_mask.shape[0] != out.shape[0]:
+            raise ValueError("nll_log_softmax: train_mask must have one entry per row of the logits")
     if n_train is None:
         n_train = int(train_mask.sum().item()) if train_mask is not None else out.shape[0]
-    return MaskedNllLogSoftmax.apply(out, labels.contiguous(), train_mask, 1.0 / float(n_train))
+    if n_train <= 0:
+        raise ValueError("nll_log_softmax: no training rows selected")
+    if out.dtype != torch.float32 or out.shape[1] > 64:
+        lp = torch.nn.functional.log_softmax(out.float(), dim=1)
+        sel = slice(None) if train_mask is None else train_mask.bool()
+        return torch.nn.functional.nll_loss(lp[sel], labels[sel], reduction="sum") / float(n_train)
+    return MaskedNllLogSoftmax.apply(out, labels, train_mask, 1.0 / float(n_train))

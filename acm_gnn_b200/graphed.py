@@ -12,7 +12,8 @@ This is the train step of the reference drivers (ACM-Pytorch/utils.py:547-574 ``
 ACM-Geometric/train.py:120-136) and their eval forward (ACM-Pytorch/train.py:110-121) for a
 FIXED set of inputs: full-batch training passes the same features, operator, labels and split
 mask every epoch.  New data (another split, new features) is written into the static tensors
-in place (``step.x.copy_(...)``, ``step.labels.copy_(...)``, ``step.train_mask.copy_(...)``).
+in place (``step.x.copy_(...)`` -- ``step.x.update_(...)`` for a StagedInput --, ``step.labels.copy_(...)``,
+``step.train_mask.copy_(...)``).
 
 Requirements: single GPU (no row partition attached); an optimizer constructed with
 ``capturable=True`` (Adam / AdamW, the reference's optimizers); dropout is supported (torch's
@@ -27,6 +28,7 @@ import torch
 from . import _lib
 from .functional import StagedInput, nll_log_softmax
 from .layers import GraphConvolution
+from .operator import AcmOperator, cached_operator
 
 
 def _check_single_gpu(model):
@@ -38,6 +40,17 @@ def _check_single_gpu(model):
 
 def _tensors_of(x):
     return x.x if isinstance(x, StagedInput) else x
+
+
+def _resolve_adj(model, adj):
+    """The captured graph bakes the device pointers of the operator's CSR arrays in, so the operator is
+    resolved ONCE here and held by a strong reference for the life of the graph (the conversion cache
+    of operator.cached_operator may evict its own reference at any time)."""
+    adj = tuple(adj)
+    if isinstance(adj[0], AcmOperator):
+        return (adj[0], None, None)
+    uses_struct = any(isinstance(m, GraphConvolution) and m._uses_structure() for m in model.modules())
+    return (cached_operator(adj[0], adj[1], adj[2] if uses_struct else None), None, None)
 
 
 class _NoTimer:
@@ -56,7 +69,9 @@ class GraphedTrainStep:
 
     model      : acm_gnn_b200.GCN (or the reference's GCN running on the drop-in layer)
     optimizer  : built with capturable=True over the model's parameters
-    x          : [N, Fin] fp32 CUDA tensor or a StagedInput (static; update in place)
+    x          : [N, Fin] fp32 CUDA tensor (static; new values with ``step.x.copy_(...)``) or a StagedInput
+                 (new values ONLY through ``step.x.update_(new_x)``, which refreshes the kernel-layout
+                 copies the captured kernels read)
     adj        : (adj_low, adj_high, adj_low_unnormalized) exactly as the reference passes them,
                  or (AcmOperator, None, None)
     labels     : int64 [N];  train_mask : uint8/bool [N] (1 = training row), the dense form of
@@ -72,7 +87,7 @@ class GraphedTrainStep:
                 raise ValueError("GraphedTrainStep needs an optimizer built with capturable=True "
                                  "(torch.optim.Adam/AdamW(..., capturable=True))")
         self.model, self.optimizer = model, optimizer
-        self.x, self.adj = x, tuple(adj)
+        self.x, self.adj = x, _resolve_adj(model, adj)
         self.labels = labels.to(torch.int64).contiguous()
         self.train_mask = train_mask.to(torch.uint8).contiguous()
         # the normaliser 1/|train| is a launch argument (host scalar) and therefore frozen in the
@@ -153,7 +168,7 @@ class GraphedForward:
         if not _tensors_of(x).is_cuda:
             raise RuntimeError("acm_gnn_b200: CUDA tensors only (there is no CPU fallback)")
         _check_single_gpu(model)
-        self.model, self.x, self.adj = model, x, tuple(adj)
+        self.model, self.x, self.adj = model, x, _resolve_adj(model, adj)
         was_training = model.training
         model.eval()
         with _NoTimer(), torch.no_grad():

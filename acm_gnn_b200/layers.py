@@ -19,7 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn.parameter import Parameter
 
-from .functional import AcmLayerFunction, LayerConfig, default_dtype
+from .functional import AcmLayerFunction, LayerConfig, default_dtype, padded_width
 from .operator import AcmOperator, cached_operator
 
 device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")  # same module-level global as the reference (layers.py:10-11)
@@ -36,7 +36,10 @@ class GraphConvolution(nn.Module):
     def __init__(self, in_features, out_features, nnodes, model_type, output_layer=0, variant=False,
                  structure_info=0):
         super().__init__()
+        if model_type not in ("mlp", "sgc", "gcn"):
+            padded_width(out_features)   # fail at construction, not in the first forward (out_features <= 256)
         self.in_features, self.out_features = in_features, out_features
+        self.nnodes = nnodes
         self.output_layer, self.model_type = output_layer, model_type
         self.structure_info, self.variant = structure_info, variant
         self.att_low, self.att_high, self.att_mlp = 0, 0, 0
@@ -73,6 +76,20 @@ class GraphConvolution(nn.Module):
         for ln in (self.layer_norm_low, self.layer_norm_high, self.layer_norm_mlp,
                    self.layer_norm_struc_low, self.layer_norm_struc_high):
             ln.reset_parameters()
+
+    # -- checkpoints: a lazily allocated (empty) struc_low stays interchangeable with the reference's ---
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        key = prefix + "struc_low"
+        t = state_dict.get(key)
+        if t is not None and self._lazy_struc and t.shape[0] != 0:
+            # reference checkpoint ([nnodes, F], unused when structure_info == 0): accept and drop it
+            state_dict = dict(state_dict)
+            state_dict[key] = t.new_empty(0, t.shape[1])
+        elif t is not None and not self._lazy_struc and t.shape[0] == 0 and not self._uses_structure():
+            # checkpoint written by a lazy layer: keep the values this (full-size, unused) parameter has
+            state_dict = dict(state_dict)
+            state_dict[key] = self.struc_low.detach()
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     # -- which branches of the reference forward are live -----------------------------------
     def _ln_live(self):

@@ -10,6 +10,7 @@ the driver passes is only validated once against ``I - A_low``.
 """
 from __future__ import annotations
 
+import collections
 import weakref
 from typing import Optional
 
@@ -298,7 +299,11 @@ def _validate_high(row, col, val, adj_high, n):
 
 
 # -- cache: the driver passes the same tensor objects every epoch ---------------------------
-_CACHE = {}
+# LRU of converted operators.  An eviction only drops the cache's own reference: whoever still holds
+# the AcmOperator (a layer call in flight, a GraphedTrainStep whose captured graph has the CSR
+# pointers baked in) keeps its device arrays alive.
+_CACHE = collections.OrderedDict()
+_CACHE_MAX = 16
 
 
 def _key(t):
@@ -315,10 +320,12 @@ def cached_operator(adj_low, adj_high, adj_low_unnormalized) -> AcmOperator:
     if hit is not None:
         op, refs = hit
         if all(r() is t for r, t in zip(refs, (adj_low, adj_high, adj_low_unnormalized)) if t is not None):
+            _CACHE.move_to_end(k)
             return op
     op = AcmOperator.from_adjacency(adj_low, adj_high, adj_low_unnormalized)
     refs = tuple(weakref.ref(t) if t is not None else (lambda: None) for t in (adj_low, adj_high, adj_low_unnormalized))
-    if len(_CACHE) > 16:
-        _CACHE.clear()
     _CACHE[k] = (op, refs)
+    _CACHE.move_to_end(k)
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)     # least recently used
     return op

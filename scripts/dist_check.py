@@ -24,13 +24,27 @@ def main():
     L.device = dev
     ok_all = True
     # hidden 64: narrow-row (smem-staged) pushes; hidden 256 + variant 1: wide-row pushes in the GEMM
-    # epilogue and in mix_bwd
-    for mode, variant, n, staged, struct, hid in (("fp32", False, 5003, False, 0, 64), ("bf16", False, 5003, False, 0, 64),
-                                                  ("fp32", True, 4096, False, 0, 64), ("fp32", False, 5003, True, 0, 64),
-                                                  ("bf16", False, 4100, True, 0, 64), ("bf16", True, 4100, False, 0, 64),
-                                                  ("fp32", False, 3001, False, 1, 64), ("bf16", True, 3001, False, 1, 64),
-                                                  ("bf16", True, 4100, False, 0, 256), ("fp32", True, 4100, False, 0, 256),
-                                                  ("bf16", False, 4100, True, 0, 256)):
+    # epilogue and in mix_bwd.  Layer 0 of every case has Fin = 48 <= 2*hidden, so by default its
+    # [HL|HH] table is built locally from the all-gathered input (functional.use_local_table) and a
+    # variant-0 layer 0 runs its backward through the input aggregation (use_input_backward);
+    # the cases with LOCAL_TABLE / BWD_INPUT = off keep the fused table push of both directions covered.
+    OLD = {"ACMB200_LOCAL_TABLE": "off", "ACMB200_BWD_INPUT": "off"}
+    NS = {"ACMB200_REORDER": "off"}                      # north-star order: transform-first in layer 0 too
+    cases = [("fp32", False, 5003, False, 0, 64, {}), ("bf16", False, 5003, False, 0, 64, {}),
+             ("fp32", True, 4096, False, 0, 64, {}), ("fp32", False, 5003, True, 0, 64, {}),
+             ("bf16", False, 4100, True, 0, 64, {}), ("bf16", True, 4100, False, 0, 64, {}),
+             ("fp32", False, 3001, False, 1, 64, {}), ("bf16", True, 3001, False, 1, 64, {}),
+             ("bf16", True, 4100, False, 0, 256, {}), ("fp32", True, 4100, False, 0, 256, {}),
+             ("bf16", False, 4100, True, 0, 256, {}),
+             ("bf16", False, 4100, True, 0, 256, NS), ("fp32", False, 5003, False, 0, 64, NS),
+             ("bf16", True, 4100, True, 0, 256, NS), ("bf16", False, 4100, False, 0, 256, NS),
+             ("bf16", True, 4100, False, 0, 256, OLD), ("fp32", False, 5003, False, 0, 64, dict(OLD, **NS)),
+             ("bf16", False, 4100, True, 0, 256, dict(OLD, **NS)), ("bf16", True, 3001, False, 1, 64, OLD)]
+    knobs = ("ACMB200_LOCAL_TABLE", "ACMB200_BWD_INPUT", "ACMB200_REORDER")
+    for mode, variant, n, staged, struct, hid, env in cases:
+        for k in knobs:
+            os.environ.pop(k, None)
+        os.environ.update(env)
         os.environ["ACMB200_DTYPE"] = mode
         fin, ncls = 48, 7
         g = torch.Generator(device=dev); g.manual_seed(5)
@@ -77,7 +91,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         ok_all = ok_all and bool(t.item())
         if rank == 0:
-            print(f"dist_check world={world} mode={mode} variant={variant} staged={staged} struct={struct} hid={hid} push={part.push_enabled()} multicast={part.multicast} n={n}: out rel.err {e_out:.2e}, worst grad rel.fro {worst:.2e} -> {'OK' if t.item() else 'FAIL'}", flush=True)
+            print(f"dist_check world={world} mode={mode} variant={variant} staged={staged} struct={struct} hid={hid} env={env} push={part.push_enabled()} multicast={part.multicast} n={n}: out rel.err {e_out:.2e}, worst grad rel.fro {worst:.2e} -> {'OK' if t.item() else 'FAIL'}", flush=True)
     if rank == 0:
         print("DIST_CHECK", "PASS" if ok_all else "FAIL", flush=True)
     dist.destroy_process_group()

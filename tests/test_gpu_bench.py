@@ -32,8 +32,13 @@ def test_bench_default_arm_contract():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["dtype"] == "bf16"
     assert d["gpu_launches"] >= 3 * 10                      # >= 10 library launches per step
     roof = d["roofline"]
-    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["achieved"] > 0
-    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9 and roof["launches_timed"] == 3
+    # this 20 k-node table (2.5 MB) is L2 resident: the bench must NOT print an HBM fraction for it,
+    # only the effective rate of the gather model; the full-size line carries achieved / frac (checked below on
+    # the arithmetic the bench uses)
+    assert roof["bound"] == "hbm" and roof["unit"] == "GB/s" and roof["launches_timed"] == 3
+    assert roof["frac"] is None and roof["achieved"] is None and roof["effective_gather_model_gbs"] > 0 and "L2" in roof["note"]
+    assert roof["algorithmic_bytes_per_launch"] > 0 and roof["avg_launch_ms"] > 0 and roof["peak"] > 1000
+    assert roof["north_star"]["kernel"].startswith("spmm_mix_fwd_kernel")
     e2e = d["e2e"]
     assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 20000 * 64 * 4 + 20000 * 8 and e2e["d2h_bytes_per_step"] == 4
     cpu = d["cpu_baseline"]
@@ -42,6 +47,10 @@ def test_bench_default_arm_contract():
     assert "workload" in d["config"] and d["loss"] == d["loss"]
     assert any(k.startswith("acm_spmm_agg_first") for k in d["kernel_ms_per_step"])
     assert d["north_star_order"]["roofline"]["achieved"] > 0
+    assert any(k.startswith("acm_spmm_mix_fwd") for k in d["north_star_order"]["kernel_ms_per_step"])
+    assert d["config"]["reference_arm_sample"].count("N=2000") == 1
+    st = d["stock_torch_gpu"]       # informational column: the unmodified reference model on this GPU via stock torch
+    assert st is not None and (st.get("value", 0) > 0 or "unavailable" in st or "error" in st), st
 
 
 def test_bench_graph_mode_contract():

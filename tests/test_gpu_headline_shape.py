@@ -1,0 +1,118 @@
+"""Parity AT THE HEADLINE SHAPE: Fin = hidden = 256, 16 classes, mean degree 20 -- the widths, degree and
+model of the bench workload (SURVEY 8d cfg 5) on the N = 100 k / E = 2 M sample that bench.py's CPU arm
+times (``cpu_step_factory``) -- instead of only on few-hundred-node graphs.  The same inputs and parameters go
+through the GPU model (fp32 and bf16 storage, aggregate-first and transform-first order, staged and raw
+input) and through the CPU oracle (oracle/acm_oracle.py, pinned to the reference by the golden vectors);
+output, loss, attention columns and EVERY gradient are compared.
+
+Stated tolerances at this size:
+  fp32 storage : the fp32 tolerance of tests/test_gpu_parity.py (max err <= 2e-5 * max|ref|, gradients 1e-4);
+  bf16 storage : forward max err <= 3e-2 * max|ref| as everywhere; gradients relative Frobenius <= 2e-2
+                 and cosine >= 0.999 per tensor -- at 10^5 nodes the bf16 storage noise of the saved
+                 activations averages out in the parameter-gradient sums, unlike on the few-hundred-node
+                 golden graphs where 0.35 is the stated (and emulated, test_bf16_noise_cpu.py) bound.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O
+
+pytestmark = pytest.mark.gpu
+
+N, E, FIN, HID, NCLS = 100_000, 2_000_000, 256, 256, 16
+BF16_FRO, BF16_COS = 2e-2, 0.999
+
+
+@pytest.fixture(scope="module")
+def workload():
+    """Inputs + the oracle's results (CPU, fp32, torch.sparse.mm COO -- the reference's own op sequence)."""
+    row, col = O.synthetic_edges(N, E, seed=0)
+    op_ref = O.build_operator(row, col, N, "pytorch")
+    low, high = O.operator_to_torch(op_ref)
+    g = torch.Generator().manual_seed(1)
+    x = O.row_normalise_features(torch.rand(N, FIN, generator=g))
+    labels = torch.randint(0, NCLS, (N,), generator=g)
+    idx = torch.randperm(N, generator=g)[: int(0.6 * N)]
+    gp = torch.Generator().manual_seed(42)
+    params = O.init_gcn_params(FIN, HID, NCLS, 0, "acmgcn", 0, gp)
+    for grp in params.values():
+        for k, t in grp.items():
+            if not k.startswith(("layer_norm", "struc", "att_struc")):
+                t.requires_grad_(True)
+    torch.set_num_threads(os.cpu_count())
+    out, atts = O.gcn_forward(params, x, low, high, None)
+    loss = O.train_step_loss(out, labels, idx)
+    loss.backward()
+    ref = {"out": out.detach(), "loss": float(loss), "atts": [a.detach() for a in atts],
+           "grads": {f"{grp}.{k}": t.grad.clone() for grp, d in params.items() for k, t in d.items() if t.grad is not None}}
+    sd = {f"{grp}.{k}": t.detach().clone() for grp, d in params.items() for k, t in d.items()}
+    return dict(row=row, col=col, op_ref=op_ref, x=x, labels=labels, idx=idx, ref=ref, sd=sd)
+
+
+def _rel(got, ref):
+    got = got.detach().double().cpu().ravel()
+    ref = ref.detach().double().cpu().ravel()
+    fro = float((got - ref).norm() / ref.norm().clamp_min(1e-300))
+    cos = float((got @ ref) / (got.norm() * ref.norm()).clamp_min(1e-300))
+    mx = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-300))
+    return fro, cos, mx
+
+
+@pytest.mark.parametrize("staged", [False, True])
+@pytest.mark.parametrize("order", ["auto", "off"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_headline_shape_matches_oracle(workload, mode, order, staged, monkeypatch):
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    from acm_gnn_b200.functional import nll_log_softmax
+    w = workload
+    monkeypatch.setenv("ACMB200_DTYPE", mode)
+    monkeypatch.setenv("ACMB200_REORDER", order)
+    op = A.AcmOperator.from_edges(torch.from_numpy(w["row"]).cuda(), torch.from_numpy(w["col"]).cuda(), N)
+    assert np.array_equal(op.low.rowptr.cpu().numpy(), w["op_ref"].rowptr)
+    assert np.array_equal(op.low.val.cpu().numpy().view(np.uint32), w["op_ref"].w_low.view(np.uint32))
+    model = A.GCN(FIN, HID, NCLS, 2, N, 0.0, "acmgcn", 0, variant=False).cuda()
+    missing, unexpected = model.load_state_dict({k: v for k, v in w["sd"].items() if not k.endswith("struc_low")}, strict=False)
+    assert not unexpected, unexpected
+    x = w["x"].cuda()
+    xin = A.stage_input(x, mode) if staged else x
+    mask = torch.zeros(N, dtype=torch.uint8, device="cuda")
+    mask[w["idx"].cuda()] = 1
+    timer = _lib.KernelTimer()
+    _lib.set_timer(timer)
+    try:
+        model.train()
+        out = model(xin, op, None, None)
+        loss = nll_log_softmax(out, w["labels"].cuda(), mask)
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        _lib.set_timer(None)
+    names = set(k.split(":")[0] for k in timer.spans)
+    assert ("acm_spmm_agg_first" in names), names          # order auto: forward; order off: input-side backward
+    ref = w["ref"]
+    tol = 2e-5 if mode == "fp32" else 3e-2
+    fro, cos, mx = _rel(out, ref["out"])
+    assert mx <= tol, f"out: max rel err {mx:.3e} ({mode}, order {order}, staged {staged})"
+    assert abs(float(loss) - ref["loss"]) <= (2e-5 if mode == "fp32" else 2e-3) * abs(ref["loss"]), (float(loss), ref["loss"])
+    for li, layer in enumerate(model.gcns):
+        att = torch.cat([layer.att_low, layer.att_high, layer.att_mlp], 1)
+        assert _rel(att, ref["atts"][li])[2] <= tol, f"att{li}"
+    report = {}
+    for k, p in model.named_parameters():
+        if k not in ref["grads"]:
+            continue
+        assert p.grad is not None, k
+        fro, cos, mx = _rel(p.grad, ref["grads"][k])
+        report[k] = (fro, cos)
+        if mode == "fp32":
+            assert fro <= 1e-4 and mx <= 1e-3, f"grad {k}: rel.fro {fro:.3e} max {mx:.3e} (fp32)"
+        else:
+            assert fro <= BF16_FRO and cos >= BF16_COS, f"grad {k}: rel.fro {fro:.3e} cos {cos:.6f} (bf16, bound {BF16_FRO})"
+    assert len(report) >= 14, sorted(report)
+    worst = max(report.items(), key=lambda kv: kv[1][0])
+    print(f"headline shape [{mode}, order {order}, staged {staged}]: out max rel err {_rel(out, ref['out'])[2]:.2e}, "
+          f"worst gradient {worst[0]} rel.fro {worst[1][0]:.2e} cos {worst[1][1]:.6f}")

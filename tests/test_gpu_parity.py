@@ -340,6 +340,50 @@ def test_aggregate_first_order_matches_oracle(fin, f, mode, monkeypatch):
     assert "acm_spmm_agg_first" not in set(k.split(":")[0] for k in timer2.spans)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("fin,f", [(7, 64), (256, 256), (100, 64), (20, 16)])
+def test_input_backward_matches_oracle(fin, f, mode, monkeypatch):
+    """Transform-first forward (ACMB200_REORDER=off: the fused gather kernel) of a variant-0 layer
+    whose input needs no gradient: the backward aggregates the layer INPUT, dW_L = (A X)^T dS_L and
+    dW_H = (X - A X)^T dS_H, instead of the transposed aggregation of [dS_L|dS_H]
+    (functional.use_input_backward).  Same gradients as the oracle; ACMB200_BWD_INPUT=off restores
+    the autograd order of the reference (transposed gather)."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    monkeypatch.setenv("ACMB200_REORDER", "off")
+    os.environ["ACMB200_DTYPE"] = mode
+    torch.manual_seed(fin * 77 + f)
+    n = 523
+    row, col = O.synthetic_edges(n - 2, 4000, seed=fin + f, zipf=0.6)
+    row = np.concatenate([row, [3, 7]])
+    col = np.concatenate([col, [3, 7]])
+    op_ref = O.build_operator(row, col, n)
+    layer = A.GraphConvolution(fin, f, n, "acmgcn", variant=False).cuda()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    x = torch.randn(n, fin)
+    w = torch.randn(n, f)
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    yo, _ = _oracle_layer(p, x.clone(), op_ref, False)
+    (yo * w).sum().backward()
+    for knob, expect_t in (("auto", False), ("off", True)):
+        monkeypatch.setenv("ACMB200_BWD_INPUT", knob)
+        layer.zero_grad(set_to_none=True)
+        timer = _lib.KernelTimer()
+        _lib.set_timer(timer)
+        try:
+            y = layer(x.cuda(), op, None, None)
+            (y * w.cuda()).sum().backward()
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_timer(None)
+        names = set(k.split(":")[0] for k in timer.spans)
+        assert ("acm_spmm_t_bwd" in names) == expect_t, names
+        assert ("acm_spmm_agg_first" in names) == (not expect_t), names
+        _close(y, yo, mode, "y")
+        for k in ("weight_low", "weight_high", "weight_mlp", "att_vec_low", "att_vec_high", "att_vec_mlp", "att_vec"):
+            _close_grad(getattr(layer, k).grad, p[k].grad, mode, f"d{k} (BWD_INPUT={knob})")
+
+
 @pytest.mark.parametrize("name", ["gcn_pt_acmgcn_v0", "gcn_geo_acmgcnp_v0_s1", "gcn_pt_acmgcnpp_v0"])
 def test_gcn_golden_with_aggregate_first(name, monkeypatch):
     """Reference golden run reproduced with the aggregate-first order in layer 0 (input

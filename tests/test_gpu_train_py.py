@@ -38,10 +38,16 @@ def test_reference_train_py_cora_unchanged(dtype):
 
 
 @pytest.mark.skipif(not os.path.exists(TRAIN), reason="reference files not staged under baseline/_ref")
-def test_reference_train_py_squirrel_acmgcnp_structure():
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_reference_train_py_squirrel_acmgcnp_structure(dtype):
     """BASELINE config 2 (Squirrel, ACM-GCN+ with structure info; published recipe
-    experiment/acmgcnp_reproduce_fixed_splits.sh:6) runs unchanged through attention4."""
+    experiment/acmgcnp_reproduce_fixed_splits.sh:6) runs unchanged through attention4.
+    Acceptance band = the unmodified reference's own result for this exact command on CPU
+    (torch 2.11, this container): test acc 0.4938 / 0.4938 / 0.4918 / 0.4899 for --seed 42 / 1 / 2 / 3
+    after the same 40 epochs on split 0.  The dropout masks (p = 0.6) come from the CUDA generator
+    here and from the CPU generator there, so the runs are not bit-comparable: require the
+    reference's accuracy minus 0.04."""
     acc, out = _run(["--dataset_name", "squirrel", "--model", "acmgcnp", "--structure_info", "1", "--variant", "0",
                      "--lr", "0.002", "--weight_decay", "1e-4", "--dropout", "0.6", "--epochs", "40",
-                     "--num_splits", "1", "--fixed_splits", "1"], "bf16")
-    assert acc > 0.20, out[-2000:]  # 5 classes: above chance after a short run
+                     "--num_splits", "1", "--fixed_splits", "1"], dtype)
+    assert acc >= 0.45, out[-2000:]
