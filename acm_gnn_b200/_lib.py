@@ -34,7 +34,8 @@ _PROTOS = {
                          _i32, _i32, _i32, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "acm_spmm_long_rows": [_i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "acm_mix_bwd": [_i32, _i32, _i32, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
-                    _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp],
+                    _i32, _i32, _i32, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp],
+    "acm_spmm_t_bwd_rank1": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "acm_gemm_xw_fwd_push": [_vp, _i64, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
     "acm_spmm_t_bwd": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "acm_nll_log_softmax": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _i64, _vp],
@@ -46,6 +47,7 @@ _PROTOS = {
     "acm_gemm_ab": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "acm_gemm_atb": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp],
     "acm_spmm_agg_first": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    "acm_fused_agg_fwd": [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "acm_spmm_plain": [_i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp],
 }
 _RESTYPES = {"acm_last_error_string": _c.c_char_p, "acm_launch_count": _i64}

@@ -112,6 +112,115 @@ spmm_t_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, 
   Slice8<T>::store(out + FP, accH);
 }
 
+// Variant 1 without LayerNorm ("rank-structured" backward table).  With the relu BEFORE the aggregation the
+// gradient rows handed to the transposed aggregation are
+//     dO_k[j,:] = c att_k[j] G[j,:] + dz_k[j] a_k^T              (k = L, H; mix_bwd, no relu mask in between)
+// so   (A^T dO_k)[i,:] = sum_j w_ji (c att_k[j]) G[j,:]  +  (sum_j w_ji dz_k[j]) a_k^T :
+// ONE gather of the G row (F wide) plus four scalars per stored edge serves BOTH channels -- half the
+// bytes of gathering [dO_L | dO_H] (2F wide), and half the exchange under a row partition.
+// Table row (written by mix_bwd in table_mode 1): T g[FP] | float {c att_L, c att_H, dz_L, dz_H}.
+template <typename T, int FP>
+__global__ void __launch_bounds__(kTWarps * 32)
+spmm_t_rank1_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                    const float* __restrict__ val, const T* __restrict__ table, const float* __restrict__ pack,
+                    const T* __restrict__ ptab, T* __restrict__ dh_all) {
+  constexpr int LANES = FP / 8;
+  constexpr int RPW = 32 / LANES;
+  constexpr int TWG = FP + 16 / (int)sizeof(T);       // row stride of the rank-1 table in elements
+  constexpr int U = 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LANES, gl = lane % LANES;
+  const int64_t row = ((int64_t)blockIdx.x * kTWarps + warp) * RPW + sub;
+  if (row >= n_rows) return;
+  int64_t e = __ldg(rowptr + row);
+  const int64_t e1 = __ldg(rowptr + row + 1);
+  const T* tab = table + gl * 8;
+  float accL[8], accH[8], sL = 0.f, sH = 0.f;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) accL[t] = accH[t] = 0.f;
+  for (; e + U <= e1; e += U) {
+    int32_t c[U];
+    float w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      c[u] = __ldg(col + e + u);
+      w[u] = val ? __ldg(val + e + u) : 1.f;
+    }
+    Slice8<T> v[U];
+    float4 sc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const T* r = table + (int64_t)c[u] * TWG;
+      v[u].load(r + gl * 8);
+      sc[u] = __ldg(reinterpret_cast<const float4*>(r + FP));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float f[8];
+      v[u].to_float(f);
+      const float wl = w[u] * sc[u].x, wh = w[u] * sc[u].y;
+      sL = fmaf(w[u], sc[u].z, sL);
+      sH = fmaf(w[u], sc[u].w, sH);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        accL[t] = fmaf(wl, f[t], accL[t]);
+        accH[t] = fmaf(wh, f[t], accH[t]);
+      }
+    }
+  }
+  for (; e < e1; ++e) {
+    const int32_t c = __ldg(col + e);
+    const float w = val ? __ldg(val + e) : 1.f;
+    const T* r = table + (int64_t)c * TWG;
+    Slice8<T> v;
+    v.load(r + gl * 8);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(r + FP));
+    float f[8];
+    v.to_float(f);
+    const float wl = w * sc.x, wh = w * sc.y;
+    sL = fmaf(w, sc.z, sL);
+    sH = fmaf(w, sc.w, sH);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      accL[t] = fmaf(wl, f[t], accL[t]);
+      accH[t] = fmaf(wh, f[t], accH[t]);
+    }
+  }
+  // own row: dO_H[i,:] = c att_H[i] G[i,:] + dz_H[i] a_H
+  float g[8], aL[8], aH[8];
+  {
+    const T* r = table + (row0 + row) * TWG;
+    Slice8<T> s;
+    s.load(r + gl * 8);
+    s.to_float(g);
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(r + FP));
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      aL[t] = __ldg(pack + pack_off_a(FP, 0) + gl * 8 + t);
+      aH[t] = __ldg(pack + pack_off_a(FP, 1) + gl * 8 + t);
+      accL[t] = fmaf(sL, aL[t], accL[t]);
+      accH[t] = fmaf(sc.y, g[t], sc.w * aH[t]) - fmaf(sH, aH[t], accH[t]);
+    }
+  }
+  if (ptab) {  // relu before the aggregation -> mask with the (relu'd) forward table
+    constexpr int TW = 2 * FP;
+    Slice8<T> a, b;
+    float pl[8], ph[8];
+    a.load(ptab + row * TW + gl * 8);
+    b.load(ptab + row * TW + FP + gl * 8);
+    a.to_float(pl);
+    b.to_float(ph);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (!(pl[t] > 0.f)) accL[t] = 0.f;
+      if (!(ph[t] > 0.f)) accH[t] = 0.f;
+    }
+  }
+  T* out = dh_all + row * (3 * FP) + gl * 8;
+  Slice8<T>::store(out, accL);
+  Slice8<T>::store(out + FP, accH);
+}
+
 template <typename T, typename TO, int FP>
 __global__ void __launch_bounds__(kTWarps * 32)
 spmm_plain_kernel(int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -388,6 +497,36 @@ extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
   if (dtype == ACM_BF16) { ACM_T_LAUNCH(__nv_bfloat16); } else { ACM_T_LAUNCH(float); }
 #undef ACM_T_LAUNCH
   ACM_LAUNCH_CHECK("spmm_t_bwd");
+  return 0;
+}
+
+extern "C" int acm_spmm_t_bwd_rank1(int dtype, int fp, int64_t n_rows, int64_t row0,
+                                    const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
+                                    const void* g_table, const float* pack, const void* p_table, void* dh_all,
+                                    void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_t_bwd_rank1: bad dtype %d", dtype);
+  ACM_CHECK_ARG(rowptr_t && col_t && g_table && pack && dh_all, "spmm_t_bwd_rank1: null pointer");
+  ACM_CHECK_ARG(fp >= 64, "spmm_t_bwd_rank1: built for padded widths >= 64 (got %d)", fp);
+  if (n_rows == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define ACM_R_LAUNCH(TT)                                                                           \
+  switch (fp) {                                                                                    \
+    case 64: { constexpr int FP = 64; ACM_R_BODY(TT) } break;                                      \
+    case 128: { constexpr int FP = 128; ACM_R_BODY(TT) } break;                                    \
+    case 256: { constexpr int FP = 256; ACM_R_BODY(TT) } break;                                    \
+    default: set_error("spmm_t_bwd_rank1: padded width %d not in {64,128,256}", fp); return ACM_ERR_UNSUPPORTED; \
+  }
+#define ACM_R_BODY(TT)                                                                             \
+    constexpr int RPB = (32 / (FP / 8)) * kTWarps;                                                 \
+    const int64_t blocks = (n_rows + RPB - 1) / RPB;                                               \
+    ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_t_bwd_rank1: too many rows");                        \
+    spmm_t_rank1_kernel<TT, FP><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                        \
+        n_rows, row0, rowptr_t, col_t, val_t, (const TT*)g_table, pack, (const TT*)p_table, (TT*)dh_all);
+  if (dtype == ACM_BF16) { ACM_R_LAUNCH(__nv_bfloat16) } else { ACM_R_LAUNCH(float) }
+#undef ACM_R_BODY
+#undef ACM_R_LAUNCH
+  ACM_LAUNCH_CHECK("spmm_t_bwd_rank1");
   return 0;
 }
 

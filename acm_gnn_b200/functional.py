@@ -122,6 +122,27 @@ def use_input_backward(cfg: LayerConfig, fin: int, fp: int, x_needs_grad: bool) 
     return padded_width(fin) <= 2 * fp
 
 
+def use_rank1_table(cfg: LayerConfig, op, fp: int) -> bool:
+    """Variant 1 (relu before the aggregation) without LayerNorm: the rows handed to the transposed
+    aggregation are dO_k = c att_k G + dz_k a_k^T, so the backward gathers (and, under a row partition,
+    exchanges) the G row plus four scalars per node instead of the 2*out_features wide [dO_L|dO_H] row --
+    half the bytes (csrc/spmm_t.cu spmm_t_rank1_kernel).  Wide rows only (padded width >= 64) and only when
+    the transposed operator has no long rows (those keep the segment-parallel pass of the plain table).
+    ``ACMB200_BWD_RANK1=off`` keeps the [dO_L|dO_H] table."""
+    return (bool(cfg.variant) and not cfg.ln_live and fp >= 64 and op.low.long_rows(True) is None
+            and _knob("ACMB200_BWD_RANK1"))
+
+
+def use_fused_forward(cfg: LayerConfig, impl: int, fp: int, f: int, k_channels: int, ldx: int) -> bool:
+    """Aggregate-first layer at out_features (padded) = 256 in bf16 storage on the tcgen05 path: one launch
+    computes [S_L|S_H|HI] = [Z W_L | D W_H | X W_I] into TMEM and applies the attention / mix epilogue from
+    there (csrc/fused_fwd.cu) -- no [S_L|S_H|HI] round trip through HBM.  Three channels without LayerNorm
+    only; y rows must be 16-byte aligned.  ``ACMB200_FUSED_FWD=off`` keeps the three GEMM launches plus the
+    pre-aggregated epilogue launch."""
+    return (impl == _lib.GEMM_TCGEN05 and cfg.dtype == "bf16" and fp == 256 and k_channels == 3 and not cfg.ln_live
+            and not cfg.variant and ldx % 8 == 0 and f % 8 == 0 and _knob("ACMB200_FUSED_FWD"))
+
+
 def use_local_table(cfg: LayerConfig, ldx: int, fp: int) -> bool:
     """Row partition, transform-first order (SURVEY 7 "what to all-gather"): exchange the NARROWER
     of {layer input X, [HL|HH] table}.  When the input row is not wider than the table row every
@@ -335,6 +356,9 @@ class AcmLayerFunction(torch.autograd.Function):
             ln_params = [(ln_flat[2 * k], ln_flat[2 * k + 1]) for k in range(K)]
         impl = cfg.gemm_impl(fin)
         x_needs_grad = bool(ctx.needs_input_grad[2])
+        # grad mode is off inside Function.forward: needs_input_grad is the reliable signal
+        # (all False under torch.no_grad(), e.g. ACM-Geometric's evaluate_acmgcn)
+        need_grad = any(ctx.needs_input_grad)
         agg_first = use_aggregate_first(cfg, fin, fp, x_needs_grad)
         bwd_input = (not agg_first) and use_input_backward(cfg, fin, fp, x_needs_grad)
         # row stride of the staged input = K extent of the transposed weights
@@ -358,6 +382,7 @@ class AcmLayerFunction(torch.autograd.Function):
             xs, x_all = _stage_rows(x, tdt, cdt, ldx, st), None
         h_i = torch.empty(n, fp, dtype=tdt, device=dev)
         z = d = wcat_t = h_lh = None
+        fused = False
         if agg_first:
             h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
             # ---- aggregate-first: Z = A X, D = X - Z, then [S_L|S_H|HI] = [Z W_L | D W_H | X W_I] ----
@@ -371,12 +396,14 @@ class AcmLayerFunction(torch.autograd.Function):
                 wp = torch.zeros(ldx, 3 * fp, dtype=tdt, device=dev)   # rows fin..ldx are zero
                 wp[:fin] = wcat
             wt = wcat_t_all  # [3fp, ldx], K-major (tcgen05 path) or None
-            for k, (a_op, c_ptr, ldc) in enumerate(((z, h_lh.data_ptr(), 2 * fp),
-                                                    (d, h_lh[:, fp:].data_ptr(), 2 * fp),
-                                                    (xs, h_i.data_ptr(), fp))):
-                _lib.call("acm_gemm_ab", impl, cdt, a_op.data_ptr(), ldx, wp[:, k * fp:].data_ptr(), 3 * fp,
-                          0 if wt is None else wt[k * fp:].data_ptr(), ldx, c_ptr, ldc, n, fp, ldx, 0, st, tag=fp)
-            del wp, wt
+            fused = use_fused_forward(cfg, impl, fp, f, K, ldx)
+            if not fused:
+                for k, (a_op, c_ptr, ldc) in enumerate(((z, h_lh.data_ptr(), 2 * fp),
+                                                        (d, h_lh[:, fp:].data_ptr(), 2 * fp),
+                                                        (xs, h_i.data_ptr(), fp))):
+                    _lib.call("acm_gemm_ab", impl, cdt, a_op.data_ptr(), ldx, wp[:, k * fp:].data_ptr(), 3 * fp,
+                              0 if wt is None else wt[k * fp:].data_ptr(), ldx, c_ptr, ldc, n, fp, ldx, 0, st, tag=fp)
+            del wp
             table, csr = h_lh, (0, 0, 0)      # pre-aggregated: only the epilogue of the fused kernel runs
             row0 = 0
             lr = (0, 0, 0, None)
@@ -434,9 +461,6 @@ class AcmLayerFunction(torch.autograd.Function):
                       op.raw.val.data_ptr(), s_tab.data_ptr(), o_s.data_ptr(), fp, fp, 1, st)
             del s_tab
 
-        # grad mode is off inside Function.forward: needs_input_grad is the reliable signal
-        # (all False under torch.no_grad(), e.g. ACM-Geometric's evaluate_acmgcn)
-        need_grad = any(ctx.needs_input_grad)
         y_bf16 = (cfg.out_dtype == "bf16")
         if y_bf16 and cfg.dtype != "bf16":
             raise ValueError("bf16 activations need ACMB200_DTYPE=bf16")
@@ -446,11 +470,19 @@ class AcmLayerFunction(torch.autograd.Function):
         # aggregate-first: the table already holds [S_L|S_H] and O_k = relu(S_k), so the table itself is
         # what the backward needs (mix_bwd applies the relu on load for variant 0) -- no second copy
         o_save = torch.empty(n, 2 * fp, dtype=tdt, device=dev) if (need_grad and not agg_first) else None
-        _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, row0, csr[0], csr[1], csr[2], 0,
-                  table.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s), pack.data_ptr(),
-                  K, int(cfg.ln_live), int(cfg.variant), float(cfg.out_scale),
-                  y.data_ptr(), _lib.ACM_BF16 if y_bf16 else _lib.ACM_F32, f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig),
-                  lr[0], lr[1], lr[2], _lib.ptr(order), st, tag=fp)
+        if fused:
+            # the three GEMMs and the attention / mix epilogue in ONE tcgen05 launch: the fp32 accumulators
+            # stay in TMEM, [S_L|S_H] and HI are written once (bf16) for the backward -- or not at all
+            _lib.call("acm_fused_agg_fwd", z.data_ptr(), d.data_ptr(), xs.data_ptr(), ldx, wt.data_ptr(), ldx, pack.data_ptr(),
+                      n, ldx, f, fp, float(cfg.out_scale), y.data_ptr(), _lib.ACM_BF16 if y_bf16 else _lib.ACM_F32, f,
+                      h_lh.data_ptr() if need_grad else 0, h_i.data_ptr() if need_grad else 0, att.data_ptr(), _lib.ptr(sig),
+                      st, tag=fp)
+        else:
+            _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, row0, csr[0], csr[1], csr[2], 0,
+                      table.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s), pack.data_ptr(),
+                      K, int(cfg.ln_live), int(cfg.variant), float(cfg.out_scale),
+                      y.data_ptr(), _lib.ACM_BF16 if y_bf16 else _lib.ACM_F32, f, _lib.ptr(o_save), att.data_ptr(), _lib.ptr(sig),
+                      lr[0], lr[1], lr[2], _lib.ptr(order), st, tag=fp)
         del lr
         if need_grad and agg_first:
             o_save = h_lh
@@ -487,21 +519,24 @@ class AcmLayerFunction(torch.autograd.Function):
         dh_all = torch.empty(n, 3 * fp, dtype=tdt, device=dev)
         dos_pre = torch.empty(n, fp, dtype=tdt, device=dev) if K == 4 else None
         dpack = torch.zeros(12 * fp + 16, dtype=torch.float32, device=dev)
-        push = (cfg.dist is not None and not ctx.agg_first and not ctx.bwd_input and cfg.dist.push_enabled())
+        needs_t = not (ctx.agg_first or ctx.bwd_input)      # a transposed aggregation follows
+        rank1 = needs_t and use_rank1_table(cfg, op, fp)
+        tw = (fp + (8 if cfg.dtype == "bf16" else 4)) if rank1 else 2 * fp     # table row width in elements
+        push = (cfg.dist is not None and needs_t and cfg.dist.push_enabled())
         if push:
             # fused mix_bwd + all-gather of the backward operand table (peer stores over NVLink)
-            t_table, hdl, ptrs, mc = cfg.dist.symm_table((cfg.layer_key, "bwd"), 2 * fp, tdt, dev)
+            t_table, hdl, ptrs, mc = cfg.dist.symm_table((cfg.layer_key, "bwd"), tw, tdt, dev)
             _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), gdt, f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
                       att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
-                      float(cfg.out_scale), 0, dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
+                      float(cfg.out_scale), 0, int(rank1), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
                       ctypes.addressof(ptrs), cfg.dist.world, op.row0, mc, st, tag=fp)
             hdl.barrier(channel=0)
             t_lh = None
         else:
-            t_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
+            t_lh = torch.empty(n, tw, dtype=tdt, device=dev)
             _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), gdt, f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
                       att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
-                      float(cfg.out_scale), t_lh.data_ptr(), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
+                      float(cfg.out_scale), t_lh.data_ptr(), int(rank1), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
                       0, 0, 0, 0, st, tag=fp)
 
         dwcat = torch.zeros(fin, 3 * fp, dtype=torch.float32, device=dev)
@@ -521,10 +556,16 @@ class AcmLayerFunction(torch.autograd.Function):
         else:
             if not push:
                 t_table = t_lh if cfg.dist is None else cfg.dist.all_gather_rows(t_lh)
-            lr = _long_pass(op.low, True, t_table, fp, 2, cdt, st)
-            _lib.call("acm_spmm_t_bwd", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
-                      op.low.val_t.data_ptr(), t_table.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(),
-                      lr[0], lr[1], lr[2], _lib.ptr(_row_order(op.low, True, fp)), st, tag=fp)
+            if rank1:
+                _lib.call("acm_spmm_t_bwd_rank1", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
+                          op.low.val_t.data_ptr(), t_table.data_ptr(), pack.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(),
+                          st, tag=fp)
+                lr = None
+            else:
+                lr = _long_pass(op.low, True, t_table, fp, 2, cdt, st)
+                _lib.call("acm_spmm_t_bwd", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
+                          op.low.val_t.data_ptr(), t_table.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(),
+                          lr[0], lr[1], lr[2], _lib.ptr(_row_order(op.low, True, fp)), st, tag=fp)
             del t_table, lr
             _lib.call("acm_gemm_bwd_dw", impl, cdt, xs.data_ptr(), ldx, dh_all.data_ptr(), dwcat.data_ptr(), n, fin, fp, st, tag=fp)
             if ctx.x_needs_grad and ctx.x_dtype == torch.bfloat16 and fin % 8 == 0:

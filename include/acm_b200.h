@@ -150,6 +150,22 @@ int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row0,
                        const void* table, void* z_out, void* d_out,
                        const int32_t* long_rows, int n_long, const float* long_acc, void* stream);
 
+/* Aggregate-first layer, out_features padded to 256, bf16 storage: the three GEMMs above AND the
+ * attention / mix epilogue of acm_spmm_mix_fwd's pre-aggregated mode in ONE tcgen05 launch
+ *   [S_L | S_H | HI] = [Z W_L | D W_H | X W_I]   (fp32 accumulators stay in TMEM)
+ *   Y = out_scale * sum_k att_k relu(.)_k ,  att = softmax(sigmoid(relu(.)_k . a_k) att_vec / 3)
+ * replacing torch.mm x3 + relu + attention3 + the mix of layers.py:163-165,188-204,94-119 without the
+ * [S_L|S_H|HI] round trip through HBM.  z, d, x: bf16 [n_rows, ldx] (k = padded input width, multiple
+ * of 8, <= 256); wcat_t: bf16 [3*fp, ldw] K-major (acm_pack_params); pack: value pack.  Outputs: y
+ * (fp32 or bf16, row stride ldy), att [n_rows,3]; for the backward (may be NULL for inference):
+ * s_lh bf16 [n_rows, 2*fp] = pre-relu [S_L|S_H], h_i bf16 [n_rows, fp], sig [n_rows,3].
+ * 3 channels, no LayerNorm, variant 0 only; returns ACM_ERR_UNSUPPORTED for fp != 256. */
+int acm_fused_agg_fwd(const void* z, const void* d, const void* x, int64_t ldx,
+                      const void* wcat_t, int64_t ldw, const float* pack,
+                      int64_t n_rows, int k, int f, int fp, float out_scale,
+                      void* y, int y_dtype, int64_t ldy, void* s_lh, void* h_i,
+                      float* att, float* sig, void* stream);
+
 /* Degree skew.  Rows with more than 256 stored edges ("long rows": local ids in long_rows,
  * ascending) are aggregated by this segment-parallel pass -- one lane group per segment
  * [seg_e0, seg_e1) of <= 256 edges, seg_long = index of the segment's row in long_rows --
@@ -207,12 +223,16 @@ int acm_set_gather_mode(int mode);
  * gradients into dpack (same layout as pack; zeroed by caller).
  * o_lh [n_rows, 2*fp]: variant 0 -> either the saved [O_L|O_H] or the pre-relu [S_L|S_H] (the
  * kernel applies the relu on load, which is the identity on already-relu'd values: the
- * aggregate-first order passes its [S_L|S_H] table and saves no second copy); variant 1 -> [O_L|O_H]. */
+ * aggregate-first order passes its [S_L|S_H] table and saves no second copy); variant 1 -> [O_L|O_H].
+ * table_mode 0: t_lh rows are [dS_L | dS_H] (2*fp wide).  table_mode 1 (variant 1 without LayerNorm,
+ * fp >= 64): the rank-structured table of acm_spmm_t_bwd_rank1 -- with the relu before the aggregation
+ * dO_k = c att_k G + dz_k a_k^T, so a row is  T g[fp] | float {c att_L, c att_H, dz_L, dz_H}
+ * (row stride fp + 16/sizeof(T) elements): half the bytes to gather and to exchange. */
 int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
                 const void* g, int g_dtype, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
                 const float* att, const float* sig, const float* pack,
                 int k_channels, int ln_live, int variant, float out_scale,
-                void* t_lh, void* dh_all, void* dos_pre, float* dpack,
+                void* t_lh, int table_mode, void* dh_all, void* dos_pre, float* dpack,
                 void* const* peer_tables, int n_peers, int64_t peer_row_off, void* multicast_table, void* stream);
 
 /* Transposed aggregation (autograd of torch.spmm(adj_low,.) / torch.spmm(adj_high,.)):
@@ -226,6 +246,15 @@ int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
                    const void* t_table, const void* p_table, void* dh_all,
                    const int32_t* long_rows, int n_long, const float* long_acc,
                    const int32_t* row_order, void* stream);
+
+/* The same transposed aggregation from the rank-structured table written by acm_mix_bwd in table_mode 1
+ * (variant 1, no LayerNorm):  (A^T dO_k)[i,:] = sum_j w_ji (c att_k[j]) G[j,:] + (sum_j w_ji dz_k[j]) a_k^T
+ * -- ONE gather of the fp-wide G row plus four scalars per stored edge serves both channels.  pack = the
+ * layer's value pack (a_L, a_H); p_table = the relu'd forward table (mask).  No long-row side pass: the
+ * caller uses acm_spmm_t_bwd when the transposed operator has rows with more than 256 edges. */
+int acm_spmm_t_bwd_rank1(int dtype, int fp, int64_t n_rows, int64_t row0,
+                         const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
+                         const void* g_table, const float* pack, const void* p_table, void* dh_all, void* stream);
 
 /* Plain single-table aggregation out = [relu](A . table), table T [*, fp]; used for the
  * structure channel relu(mm(adj_low_unnormalized, struc_low)) (layers.py:207-209) and its

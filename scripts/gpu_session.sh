@@ -4,6 +4,7 @@
 # Outputs go to gpurun_out/<TAG>_*.  Steps:
 #   tests            pytest -m gpu (-x, as the driver runs it)
 #   tests:<expr>     pytest -m gpu -k <expr>
+#   qtests:<expr>    the same with a 300 s guard; aborts the rest of the session when it fails (new kernels)
 #   smoke            __graft_entry__.build() + smoke()
 #   ref              bench.py --impl reference (3 steps)
 #   bench[:args]     bench.py [args]                      (single GPU; args comma separated, e.g. bench:--config,cfg3)
@@ -39,6 +40,10 @@ for STEP in "$@"; do
       if [ -n "$REST" ]; then timeout 1500 python -m pytest tests -x -q -m gpu -k "$REST" -s > ${O}_pytest_$i.log 2>&1
       else timeout 1700 python -m pytest tests -x -q -m gpu > ${O}_pytest_$i.log 2>&1; fi
       echo "=== [$STEP] rc=$?"; tail -5 ${O}_pytest_$i.log; grep -E "headline shape|ref_model_check" ${O}_pytest_$i.log | tail -20 ;;
+    qtests)   # quick, guarded run of a few tests (new kernels): short timeout, abort the session on failure
+      timeout 300 python -m pytest tests -x -q -m gpu -k "$REST" -s --timeout 120 > ${O}_qtests_$i.log 2>&1; RC=$?
+      echo "=== [$STEP] rc=$RC"; tail -15 ${O}_qtests_$i.log | cut -c1-400
+      if [ $RC -ne 0 ]; then echo "aborting session: guarded tests failed"; exit 0; fi ;;
     smoke)
       timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > ${O}_smoke.log 2>&1; echo "=== [smoke] rc=$?"; tail -3 ${O}_smoke.log ;;
     ref)

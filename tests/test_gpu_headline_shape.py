@@ -5,12 +5,19 @@ through the GPU model (fp32 and bf16 storage, aggregate-first and transform-firs
 input) and through the CPU oracle (oracle/acm_oracle.py, pinned to the reference by the golden vectors);
 output, loss, attention columns and EVERY gradient are compared.
 
+The oracle runs twice: in fp32 (the reference's arithmetic) and in fp64 ("truth").  Sums over 10^5 rows make
+the fp32 oracle itself inexact (the high-pass weight gradient is a cancelling sum: measured 1e-4..4e-4
+relative), so gradients are judged against the fp64 run.
+
 Stated tolerances at this size:
-  fp32 storage : the fp32 tolerance of tests/test_gpu_parity.py (max err <= 2e-5 * max|ref|, gradients 1e-4);
+  fp32 storage : output / attention max err <= 2e-5 * max|ref| vs the fp32 oracle; every gradient at most
+                 4x as far from the fp64 truth as the fp32 ORACLE is (floor 2e-5 relative Frobenius) --
+                 i.e. the kernels are as accurate as the reference's own fp32 op sequence;
   bf16 storage : forward max err <= 3e-2 * max|ref| as everywhere; gradients relative Frobenius <= 2e-2
-                 and cosine >= 0.999 per tensor -- at 10^5 nodes the bf16 storage noise of the saved
-                 activations averages out in the parameter-gradient sums, unlike on the few-hundred-node
-                 golden graphs where 0.35 is the stated (and emulated, test_bf16_noise_cpu.py) bound.
+                 and cosine >= 0.999 per tensor vs fp64 -- at 10^5 nodes the bf16 storage noise of the
+                 saved activations averages out in the parameter-gradient sums, unlike on the
+                 few-hundred-node golden graphs where 0.35 is the stated (and emulated,
+                 test_bf16_noise_cpu.py) bound.
 """
 import os
 
@@ -38,18 +45,23 @@ def workload():
     idx = torch.randperm(N, generator=g)[: int(0.6 * N)]
     gp = torch.Generator().manual_seed(42)
     params = O.init_gcn_params(FIN, HID, NCLS, 0, "acmgcn", 0, gp)
-    for grp in params.values():
-        for k, t in grp.items():
-            if not k.startswith(("layer_norm", "struc", "att_struc")):
-                t.requires_grad_(True)
     torch.set_num_threads(os.cpu_count())
-    out, atts = O.gcn_forward(params, x, low, high, None)
-    loss = O.train_step_loss(out, labels, idx)
-    loss.backward()
-    ref = {"out": out.detach(), "loss": float(loss), "atts": [a.detach() for a in atts],
-           "grads": {f"{grp}.{k}": t.grad.clone() for grp, d in params.items() for k, t in d.items() if t.grad is not None}}
+
+    def run(dt):
+        ps = {grp: {k: t.detach().to(dt).clone() for k, t in d.items()} for grp, d in params.items()}
+        for grp in ps.values():
+            for k, t in grp.items():
+                if not k.startswith(("layer_norm", "struc", "att_struc")):
+                    t.requires_grad_(True)
+        out, atts = O.gcn_forward(ps, x.to(dt), low.to(dt), high.to(dt), None)
+        loss = O.train_step_loss(out, labels, idx)
+        loss.backward()
+        return {"out": out.detach(), "loss": float(loss), "atts": [a.detach() for a in atts],
+                "grads": {f"{grp}.{k}": t.grad.clone() for grp, d in ps.items() for k, t in d.items() if t.grad is not None}}
+
+    ref, ref64 = run(torch.float32), run(torch.float64)
     sd = {f"{grp}.{k}": t.detach().clone() for grp, d in params.items() for k, t in d.items()}
-    return dict(row=row, col=col, op_ref=op_ref, x=x, labels=labels, idx=idx, ref=ref, sd=sd)
+    return dict(row=row, col=col, op_ref=op_ref, x=x, labels=labels, idx=idx, ref=ref, ref64=ref64, sd=sd)
 
 
 def _rel(got, ref):
@@ -106,10 +118,13 @@ def test_headline_shape_matches_oracle(workload, mode, order, staged, monkeypatc
         if k not in ref["grads"]:
             continue
         assert p.grad is not None, k
-        fro, cos, mx = _rel(p.grad, ref["grads"][k])
+        truth = w["ref64"]["grads"][k]
+        fro, cos, mx = _rel(p.grad, truth)
         report[k] = (fro, cos)
         if mode == "fp32":
-            assert fro <= 1e-4 and mx <= 1e-3, f"grad {k}: rel.fro {fro:.3e} max {mx:.3e} (fp32)"
+            fro_ref = _rel(ref["grads"][k], truth)[0]          # how inexact the reference's own fp32 arithmetic is
+            assert fro <= max(4 * fro_ref, 2e-5), f"grad {k}: rel.fro vs fp64 {fro:.3e}, fp32 oracle {fro_ref:.3e}"
+            assert _rel(p.grad, ref["grads"][k])[0] <= 2e-3, f"grad {k} vs fp32 oracle"
         else:
             assert fro <= BF16_FRO and cos >= BF16_COS, f"grad {k}: rel.fro {fro:.3e} cos {cos:.6f} (bf16, bound {BF16_FRO})"
     assert len(report) >= 14, sorted(report)

@@ -384,6 +384,124 @@ def test_input_backward_matches_oracle(fin, f, mode, monkeypatch):
             _close_grad(getattr(layer, k).grad, p[k].grad, mode, f"d{k} (BWD_INPUT={knob})")
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("f", [64, 100, 256])
+def test_rank1_backward_table_matches_oracle(f, mode, monkeypatch):
+    """Variant 1 without LayerNorm: dO_k = c att_k G + dz_k a_k^T, so the transposed aggregation gathers the G row
+    plus four scalars (acm_spmm_t_bwd_rank1) instead of the [dO_L|dO_H] row (acm_spmm_t_bwd).  Both knob settings
+    must match the oracle; in fp32 they must also agree with each other to rounding."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    os.environ["ACMB200_DTYPE"] = mode
+    torch.manual_seed(f)
+    n, fin = 777, 40
+    row, col = O.synthetic_edges(n - 1, 9000, seed=f, zipf=0.5)     # last node isolated
+    row = np.concatenate([row, [11]])
+    col = np.concatenate([col, [11]])                                 # one data self-loop
+    op_ref = O.build_operator(row, col, n)
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    assert op.low.long_rows(True) is None
+    layer = A.GraphConvolution(fin, f, n, "acmgcn", variant=True).cuda()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    x = torch.randn(n, fin)
+    w = torch.randn(n, f)
+    xo = x.clone().requires_grad_(True)
+    yo, _ = _oracle_layer(p, xo, op_ref, True)
+    (yo * w).sum().backward()
+    got = {}
+    for knob in ("auto", "off"):
+        monkeypatch.setenv("ACMB200_BWD_RANK1", knob)
+        layer.zero_grad(set_to_none=True)
+        xc = x.clone().cuda().requires_grad_(True)
+        timer = _lib.KernelTimer()
+        _lib.set_timer(timer)
+        try:
+            y = layer(xc, op, None, None)
+            (y * w.cuda()).sum().backward()
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_timer(None)
+        names = set(k.split(":")[0] for k in timer.spans)
+        assert ("acm_spmm_t_bwd_rank1" in names) == (knob == "auto") and ("acm_spmm_t_bwd" in names) == (knob == "off"), names
+        _close(y, yo, mode, "y")
+        _close_grad(xc.grad, xo.grad, mode, f"dx ({knob})")
+        for k in ("weight_low", "weight_high", "weight_mlp", "att_vec_low", "att_vec_high", "att_vec_mlp", "att_vec"):
+            _close_grad(getattr(layer, k).grad, p[k].grad, mode, f"d{k} ({knob})")
+        got[knob] = (xc.grad.clone(), layer.weight_low.grad.clone(), layer.weight_high.grad.clone())
+    if mode == "fp32":
+        for a, b in zip(got["auto"], got["off"]):
+            assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
+
+
+@pytest.mark.parametrize("y_bf16", [False, True])
+@pytest.mark.parametrize("n,fin,f", [(1000, 256, 256), (4133, 48, 256), (129, 8, 200), (77, 100, 256)])
+def test_fused_tcgen05_forward_matches_unfused(n, fin, f, y_bf16, monkeypatch):
+    """csrc/fused_fwd.cu (three tcgen05 GEMMs + attention/mix epilogue in one launch, accumulators in TMEM)
+    against the unfused aggregate-first path (three GEMM launches that round [S_L|S_H|HI] to bf16 + epilogue
+    launch) and against the oracle: forward within the bf16 tolerance, attention columns close, saved tables
+    equivalent (same gradients within bf16 noise).  Partial last tile (n not a multiple of 128), several tiles
+    per SM, K < 64 and out_features < 256 (partial output chunks) are all exercised."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    monkeypatch.setenv("ACMB200_REORDER", "auto")
+    os.environ["ACMB200_DTYPE"] = "bf16"
+    torch.manual_seed(n + fin)
+    row, col = O.synthetic_edges(n, 12 * n, seed=n)
+    op_ref = O.build_operator(row, col, n)
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    layer = A.GraphConvolution(fin, f, n, "acmgcn", variant=False).cuda()
+    if y_bf16:
+        layer.acm_out_dtype = "bf16"
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in layer.state_dict().items()}
+    x = torch.randn(n, fin)
+    w = torch.randn(n, f)
+    res = {}
+    for knob in ("auto", "off"):
+        monkeypatch.setenv("ACMB200_FUSED_FWD", knob)
+        layer.zero_grad(set_to_none=True)
+        timer = _lib.KernelTimer()
+        _lib.set_timer(timer)
+        try:
+            y = layer(x.cuda(), op, None, None)
+            (y.float() * w.cuda()).sum().backward()
+            torch.cuda.synchronize()
+        finally:
+            _lib.set_timer(None)
+        names = set(k.split(":")[0] for k in timer.spans)
+        assert ("acm_fused_agg_fwd" in names) == (knob == "auto" and f % 8 == 0), names
+        assert y.dtype == (torch.bfloat16 if y_bf16 else torch.float32)
+        res[knob] = (y.detach().float().clone(), torch.cat([layer.att_low, layer.att_high, layer.att_mlp], 1).clone(),
+                     {k: getattr(layer, k).grad.detach().clone() for k in ("weight_low", "weight_high", "weight_mlp", "att_vec_low", "att_vec")})
+    yo, atto = _oracle_layer(p, x.clone(), op_ref, False)
+    (yo * w).sum().backward()
+    for knob in ("auto", "off"):
+        _close(res[knob][0], yo, "bf16", f"y ({knob})")
+        _close(res[knob][1], atto, "bf16", f"att ({knob})")
+        for k, g in res[knob][2].items():
+            _close_grad(g, p[k].grad, "bf16", f"d{k} ({knob})")
+    # fused vs unfused: same math, the fused epilogue sees the fp32 accumulators instead of their bf16 rounding
+    scale = float(res["off"][0].abs().max())
+    assert float((res["auto"][0] - res["off"][0]).abs().max()) <= 2e-2 * scale
+    assert float((res["auto"][1] - res["off"][1]).abs().max()) <= 2e-2
+
+
+def test_fused_tcgen05_forward_inference_saves_nothing(monkeypatch):
+    """Under torch.no_grad the fused kernel gets NULL table / h_i / sig pointers and must give the same output."""
+    import acm_gnn_b200 as A
+    monkeypatch.setenv("ACMB200_REORDER", "auto")
+    os.environ["ACMB200_DTYPE"] = "bf16"
+    torch.manual_seed(5)
+    n = 3000
+    row, col = O.synthetic_edges(n, 30000, seed=2)
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    layer = A.GraphConvolution(64, 256, n, "acmgcn", variant=False).cuda()
+    x = torch.rand(n, 64, device="cuda")
+    y_train = layer(x, op, None, None)
+    with torch.no_grad():
+        y_eval = layer(x, op, None, None)
+    assert torch.equal(y_train.detach(), y_eval)
+
+
 @pytest.mark.parametrize("name", ["gcn_pt_acmgcn_v0", "gcn_geo_acmgcnp_v0_s1", "gcn_pt_acmgcnpp_v0"])
 def test_gcn_golden_with_aggregate_first(name, monkeypatch):
     """Reference golden run reproduced with the aggregate-first order in layer 0 (input
