@@ -133,6 +133,9 @@ def use_rank1_table(cfg: LayerConfig, op, fp: int) -> bool:
             and _knob("ACMB200_BWD_RANK1"))
 
 
+FUSED_FWD_DEFAULT = "off"     # opt-in until it beats the unfused launches (profiles/: 11.7 vs 10.5 ms at the headline size)
+
+
 def use_fused_forward(cfg: LayerConfig, impl: int, fp: int, f: int, k_channels: int, ldx: int) -> bool:
     """Aggregate-first layer at out_features (padded) = 256 in bf16 storage on the tcgen05 path: one launch
     computes [S_L|S_H|HI] = [Z W_L | D W_H | X W_I] into TMEM and applies the attention / mix epilogue from
@@ -140,7 +143,7 @@ def use_fused_forward(cfg: LayerConfig, impl: int, fp: int, f: int, k_channels: 
     only; y rows must be 16-byte aligned.  ``ACMB200_FUSED_FWD=off`` keeps the three GEMM launches plus the
     pre-aggregated epilogue launch."""
     return (impl == _lib.GEMM_TCGEN05 and cfg.dtype == "bf16" and fp == 256 and k_channels == 3 and not cfg.ln_live
-            and not cfg.variant and ldx % 8 == 0 and f % 8 == 0 and _knob("ACMB200_FUSED_FWD"))
+            and not cfg.variant and ldx % 8 == 0 and f % 8 == 0 and _knob("ACMB200_FUSED_FWD", FUSED_FWD_DEFAULT))
 
 
 def use_local_table(cfg: LayerConfig, ldx: int, fp: int) -> bool:

@@ -395,9 +395,10 @@ def test_rank1_backward_table_matches_oracle(f, mode, monkeypatch):
     os.environ["ACMB200_DTYPE"] = mode
     torch.manual_seed(f)
     n, fin = 777, 40
-    row, col = O.synthetic_edges(n - 1, 9000, seed=f, zipf=0.5)     # last node isolated
-    row = np.concatenate([row, [11]])
-    col = np.concatenate([col, [11]])                                 # one data self-loop
+    row, col = O.synthetic_edges(n - 1, 9000, seed=f)               # last node isolated
+    hub = np.arange(1, 150)                                           # a hub below the long-row threshold (256)
+    row = np.concatenate([row, np.zeros_like(hub), hub, [11]])
+    col = np.concatenate([col, hub, np.zeros_like(hub), [11]])        # + one data self-loop
     op_ref = O.build_operator(row, col, n)
     op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
     assert op.low.long_rows(True) is None
