@@ -34,8 +34,8 @@ _PROTOS = {
                          _i32, _i32, _i32, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "acm_spmm_long_rows": [_i32, _i32, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "acm_mix_bwd": [_i32, _i32, _i32, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
-                    _i32, _i32, _i32, _f32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp],
-    "acm_spmm_t_bwd_rank1": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+                    _i32, _i32, _i32, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp],
+    "acm_spmm_t_bwd_rank1": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "acm_gemm_xw_fwd_push": [_vp, _i64, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
     "acm_spmm_t_bwd": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "acm_nll_log_softmax": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _i64, _vp],

@@ -11,15 +11,19 @@
 //
 // TMEM plan (512 columns = two regions of 256):   R0 = cols [0,256)   R1 = cols [256,512)
 //   MMA warp     : HI -> R0, S_L -> R1, (wait: R0 drained) S_H -> R0
-//   epilogue     : drain HI from R0 into REGISTERS (bf16 pairs: 64 registers per thread hold the
-//                  thread's half row) while S_L is being accumulated; logits of S_L while S_H is being
-//                  accumulated; logits of S_H; softmax; second pass over R1/R0 + the HI registers for Y.
+//   epilogue     : drain HI from R0 (identity logit; written to h_i as bf16, the form the backward reads) while
+//                  S_L is being accumulated; logits of S_L while S_H is being accumulated; logits of S_H;
+//                  softmax; second pass over R1/R0 for Y, with the thread's HI values read back from the h_i
+//                  rows this same warp has just written (L2 hits, one full 32-byte sector per load pair).
 //   In the TMEM accumulator layout one thread owns one row (lane = row), so the three dot products,
-//   the softmax and the mix are thread-local; the two warps of a lane quadrant split the 256 columns
-//   of every channel in halves and exchange their three partial logits through shared memory.
+//   the softmax and the mix are thread-local; the FOUR warps of a lane quadrant split the 256 columns
+//   of every channel in quarters and exchange their three partial logits through shared memory.
+//   (A first version with two warps per quadrant that kept HI in 64 registers per thread was latency
+//   bound -- 8 warps, 3.5 k dependent instructions each per tile, issue slots 20 % busy: 11.7 ms against
+//   10.5 ms for the unfused launches, profiles/r2d_*.  Sixteen epilogue warps hide those latencies.)
 //
-// Warps: 0 = TMA producer (4-stage ring of {A 128x64, B 256x64} bf16 tiles, 128B swizzle),
-//        1 = MMA issuer + TMEM owner, 2..9 = epilogue (warp w: lane quadrant w & 3, column half (w-2) >> 2).
+// Warps: 0 = TMA producer (3-stage ring of {A 128x64, B 256x64} bf16 tiles, 128B swizzle),
+//        1 = MMA issuer + TMEM owner, 2..17 = epilogue (warp w: lane quadrant w & 3, column quarter (w-2) >> 2).
 // All global stores go through a per-warp transposition tile so that every store instruction writes
 // full 32-byte sectors of row-contiguous bytes.
 #include <cuda.h>
@@ -33,8 +37,10 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int FP = 256;                   // out_features (padded): the only width this kernel is built for
-constexpr int kStages = 4;
-constexpr int kEpiWarps = 8;
+constexpr int kStages = 3;
+constexpr int kParts = 4;                 // column parts per channel = epilogue warps per TMEM lane quadrant
+constexpr int kEpiWarps = 4 * kParts;
+constexpr int CW = FP / kParts;           // columns of every channel owned by one epilogue warp
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK * 2;           // 16 KB
 constexpr uint32_t kBBytes = FP * BK * 2;           // 32 KB
@@ -94,14 +100,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* r) {
   tmem_ld32_issue(taddr, r);
   tmem_wait_ld();
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* r) {
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]),
         "=f"(r[8]), "=f"(r[9]), "=f"(r[10]), "=f"(r[11]), "=f"(r[12]), "=f"(r[13]), "=f"(r[14]), "=f"(r[15])
       : "r"(taddr) : "memory");
-  tmem_wait_ld();
 }
 // sm_100 UMMA shared-memory descriptor, K-major operand, 128B swizzle (same encoding as gemm_tc.cu)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -136,7 +141,7 @@ struct Params {
   float out_scale;
   void* y; int y_bf16; int64_t ldy;
   __nv_bfloat16* s_lh;  // [n, 512] = [S_L | S_H] (pre-relu), or nullptr (inference)
-  __nv_bfloat16* h_i;   // [n, 256] pre-relu HI, or nullptr
+  __nv_bfloat16* h_i;   // [n, 256] pre-relu HI (always written: the second pass reads it back)
   float* att; float* sig;
 };
 
@@ -163,28 +168,29 @@ __device__ __forceinline__ void store_rows64(uint8_t* stg, const uint32_t (&w)[1
 
 // sum_j relu(acc[row, j]) * a[j] over this warp's 128 columns of one channel (thread = row); the raw
 // (pre-relu) accumulator chunk goes to the backward's table on the way (tab = nullptr: inference)
-__device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, uint8_t* stg, __nv_bfloat16* tab, int rows_ok, int lane) {
-  float acc = 0.f;
+__device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, uint8_t* stg, __nv_bfloat16* tab, int64_t ld_bytes,
+                                         int rows_ok, int lane) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent FMA chains
 #pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
+  for (int cc = 0; cc < CW / 32; ++cc) {
     float v[32];
     tmem_ld32(taddr + (uint32_t)(cc * 32), v);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 av = *reinterpret_cast<const float4*>(a + cc * 32 + j);
-      acc = fmaf(fmaxf(v[j], 0.f), av.x, acc);
-      acc = fmaf(fmaxf(v[j + 1], 0.f), av.y, acc);
-      acc = fmaf(fmaxf(v[j + 2], 0.f), av.z, acc);
-      acc = fmaf(fmaxf(v[j + 3], 0.f), av.w, acc);
+      a0 = fmaf(fmaxf(v[j], 0.f), av.x, a0);
+      a1 = fmaf(fmaxf(v[j + 1], 0.f), av.y, a1);
+      a2 = fmaf(fmaxf(v[j + 2], 0.f), av.z, a2);
+      a3 = fmaf(fmaxf(v[j + 3], 0.f), av.w, a3);
     }
     if (tab) {
       uint32_t w16[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) w16[j] = pack2(v[2 * j], v[2 * j + 1]);
-      store_rows64(stg, w16, reinterpret_cast<uint8_t*>(tab + cc * 32), (int64_t)FP * 4, rows_ok, lane);
+      store_rows64(stg, w16, reinterpret_cast<uint8_t*>(tab + cc * 32), ld_bytes, rows_ok, lane);
     }
   }
-  return acc;
+  return (a0 + a1) + (a2 + a3);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -193,12 +199,12 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  // ring | staging | a_k [3][256] f32 | avec [16] f32 | z exchange [2][2][128][4] f32 | barriers
+  // ring | staging | a_k [3][256] f32 | avec [16] f32 | z exchange [2][kParts][128][4] f32 | barriers
   const uint32_t off_stg = kStages * kStageBytes;
   const uint32_t off_a = off_stg + kEpiWarps * kStgBytes;
   const uint32_t off_avec = off_a + 3 * FP * 4;
   const uint32_t off_z = off_avec + 64;
-  const uint32_t off_bar = off_z + 2 * 2 * BM * 16;
+  const uint32_t off_bar = off_z + 2 * kParts * BM * 16;
   const uint32_t bar_full = base + off_bar;                // [kStages]
   const uint32_t bar_empty = bar_full + 8 * kStages;       // [kStages]
   const uint32_t bar_acc = bar_empty + 8 * kStages;        // [3]: HI, S_L, S_H accumulators complete
@@ -294,10 +300,10 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       }
     }
   } else {
-    // ---------------- epilogue: thread = row (TMEM lane), warp pair of a quadrant splits the columns
+    // ---------------- epilogue: thread = row (TMEM lane), the kParts warps of a quadrant split the columns
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int c_lo = half * (FP / 2);
+    const int part = (warp - 2) >> 2;
+    const int c_lo = part * CW;
     uint8_t* stg = gbase + off_stg + (warp - 2) * kStgBytes;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float inv_k = 1.f / 3.f;
@@ -308,57 +314,37 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       const int64_t row = row_w0 + lane;
       int rows_ok = (int)((p.n - row_w0) < 32 ? (p.n - row_w0) : 32);
       if (rows_ok < 0) rows_ok = 0;
-      float zp[3] = {0.f, 0.f, 0.f};
-      uint32_t hi[FP / 4];                                 // this thread's half row of HI as bf16 pairs
 
-      // ---- HI: R0 -> registers (+ h_i store), identity logit
+      // ---- HI: R0 -> h_i (bf16), identity logit
       mbar_wait(bar_acc + 0, tp);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        float v[32];
-        tmem_ld32(lane_addr + (uint32_t)(c_lo + cc * 32), v);
-        const float* a = s_a + 2 * FP + c_lo + cc * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 av = *reinterpret_cast<const float4*>(a + j);
-          zp[2] = fmaf(fmaxf(v[j], 0.f), av.x, zp[2]);
-          zp[2] = fmaf(fmaxf(v[j + 1], 0.f), av.y, zp[2]);
-          zp[2] = fmaf(fmaxf(v[j + 2], 0.f), av.z, zp[2]);
-          zp[2] = fmaf(fmaxf(v[j + 3], 0.f), av.w, zp[2]);
-        }
-        uint32_t w16[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          w16[j] = pack2(v[2 * j], v[2 * j + 1]);
-          hi[cc * 16 + j] = w16[j];
-        }
-        if (p.h_i)
-          store_rows64(stg, w16, reinterpret_cast<uint8_t*>(p.h_i + row_w0 * FP + c_lo + cc * 32), (int64_t)FP * 2, rows_ok, lane);
-      }
+      const float zI = row_dot(lane_addr + (uint32_t)c_lo, s_a + 2 * FP + c_lo, stg, p.h_i + row_w0 * FP + c_lo,
+                               (int64_t)FP * 2, rows_ok, lane);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_r0);
 
-      // ---- logits of S_L (R1) while S_H is being accumulated, then of S_H (R0)
+      // ---- logits of S_L (R1) while S_H is being accumulated, then of S_H (R0); raw accumulators -> table
       mbar_wait(bar_acc + 8, tp);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      zp[0] = row_dot(lane_addr + (uint32_t)(FP + c_lo), s_a + c_lo, stg,
-                      p.s_lh ? p.s_lh + row_w0 * (2 * FP) + c_lo : nullptr, rows_ok, lane);
+      const float zL = row_dot(lane_addr + (uint32_t)(FP + c_lo), s_a + c_lo, stg,
+                               p.s_lh ? p.s_lh + row_w0 * (2 * FP) + c_lo : nullptr, (int64_t)FP * 4, rows_ok, lane);
       mbar_wait(bar_acc + 16, tp);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      zp[1] = row_dot(lane_addr + (uint32_t)c_lo, s_a + FP + c_lo, stg,
-                      p.s_lh ? p.s_lh + row_w0 * (2 * FP) + FP + c_lo : nullptr, rows_ok, lane);
+      const float zH = row_dot(lane_addr + (uint32_t)c_lo, s_a + FP + c_lo, stg,
+                               p.s_lh ? p.s_lh + row_w0 * (2 * FP) + FP + c_lo : nullptr, (int64_t)FP * 4, rows_ok, lane);
 
-      // ---- combine the two column halves, attention
-      float* zx = s_z + ((tp * 2 + half) * BM + q * 32 + lane) * 4;
-      *reinterpret_cast<float4*>(zx) = make_float4(zp[0], zp[1], zp[2], 0.f);
-      named_sync(1 + q, 64);
-      const float4 zo = *reinterpret_cast<const float4*>(s_z + ((tp * 2 + (half ^ 1)) * BM + q * 32 + lane) * 4);
-      // identical summation order in both warps of the pair (half 0 + half 1)
-      const float z0 = half ? zo.x + zp[0] : zp[0] + zo.x;
-      const float z1 = half ? zo.y + zp[1] : zp[1] + zo.y;
-      const float z2 = half ? zo.z + zp[2] : zp[2] + zo.z;
+      // ---- combine the column parts (fixed order: identical sums in every warp of the quadrant), attention
+      *reinterpret_cast<float4*>(s_z + ((tp * kParts + part) * BM + q * 32 + lane) * 4) = make_float4(zL, zH, zI, 0.f);
+      named_sync(1 + q, 32 * kParts);
+      float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < kParts; ++pp) {
+        const float4 zo = *reinterpret_cast<const float4*>(s_z + ((tp * kParts + pp) * BM + q * 32 + lane) * 4);
+        z0 += zo.x;
+        z1 += zo.y;
+        z2 += zo.z;
+      }
       float sgm[3], al[3];
       sgm[0] = __fdividef(1.f, 1.f + __expf(-z0));
       sgm[1] = __fdividef(1.f, 1.f + __expf(-z1));
@@ -381,66 +367,67 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       const float rden = __fdividef(1.f, den);
 #pragma unroll
       for (int k = 0; k < 3; ++k) al[k] *= rden;
-      if (row < p.n) {
-        float* dst = half == 0 ? p.att : p.sig;
+      if (row < p.n && part < 2) {
+        float* dst = part == 0 ? p.att : p.sig;
         if (dst) {
-          dst[row * 3 + 0] = half == 0 ? al[0] : sgm[0];
-          dst[row * 3 + 1] = half == 0 ? al[1] : sgm[1];
-          dst[row * 3 + 2] = half == 0 ? al[2] : sgm[2];
+          dst[row * 3 + 0] = part == 0 ? al[0] : sgm[0];
+          dst[row * 3 + 1] = part == 0 ? al[1] : sgm[1];
+          dst[row * 3 + 2] = part == 0 ? al[2] : sgm[2];
         }
       }
       const float cL = p.out_scale * al[0], cH = p.out_scale * al[1], cI = p.out_scale * al[2];
 
-      // ---- second pass: Y = c (att_L relu(S_L) + att_H relu(S_H) + att_I relu(HI))
+      // ---- second pass: Y = c (att_L relu(S_L) + att_H relu(S_H) + att_I relu(HI)), 16 columns at a time;
+      // HI comes back from the h_i rows this warp stored above (same warp, __syncwarp in store_rows64)
+      const __nv_bfloat16* hrow = p.h_i + (row < p.n ? row : 0) * FP;
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c0 = c_lo + cc * 32;
-        float vl[32];
+      for (int cc = 0; cc < CW / 32; ++cc) {
         uint32_t w16[16];
-        tmem_ld32(lane_addr + (uint32_t)(FP + c0), vl);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float2 h2 = unpack2(hi[cc * 16 + j]);
-          vl[2 * j] = fmaf(cL, fmaxf(vl[2 * j], 0.f), cI * fmaxf(h2.x, 0.f));
-          vl[2 * j + 1] = fmaf(cL, fmaxf(vl[2 * j + 1], 0.f), cI * fmaxf(h2.y, 0.f));
-        }
+        const bool chunk_full = c_lo + cc * 32 + 32 <= p.f;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          float vh[16];
-          tmem_ld16(lane_addr + (uint32_t)(c0 + hh * 16), vh);
+          const int c0 = c_lo + cc * 32 + hh * 16;
+          const uint4 h0 = __ldcg(reinterpret_cast<const uint4*>(hrow + c0));
+          const uint4 h1 = __ldcg(reinterpret_cast<const uint4*>(hrow + c0 + 8));
+          float vl[16], vh[16];
+          tmem_ld16_issue(lane_addr + (uint32_t)(FP + c0), vl);
+          tmem_ld16_issue(lane_addr + (uint32_t)c0, vh);
+          tmem_wait_ld();
+          const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-          for (int j = 0; j < 16; ++j) vl[hh * 16 + j] = fmaf(cH, fmaxf(vh[j], 0.f), vl[hh * 16 + j]);
-        }
-        // columns >= f are padding (zero weights): never stored
-        if (p.y_bf16) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) w16[j] = pack2(vl[2 * j], vl[2 * j + 1]);
-          if (c0 + 32 <= p.f) {
-            store_rows64(stg, w16, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.y) + row_w0 * p.ldy + c0),
-                         p.ldy * 2, rows_ok, lane);
-          } else if (row < p.n) {
-            __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + j < p.f) yr[c0 + j] = __float2bfloat16_rn(vl[j]);
+          for (int j = 0; j < 8; ++j) {
+            const float2 h2 = unpack2(hw[j]);
+            vl[2 * j] = fmaf(cL, fmaxf(vl[2 * j], 0.f), fmaf(cH, fmaxf(vh[2 * j], 0.f), cI * fmaxf(h2.x, 0.f)));
+            vl[2 * j + 1] = fmaf(cL, fmaxf(vl[2 * j + 1], 0.f), fmaf(cH, fmaxf(vh[2 * j + 1], 0.f), cI * fmaxf(h2.y, 0.f)));
           }
-        } else {
+          // columns >= f are padding (zero weights): never stored
+          if (p.y_bf16) {
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const int cq = c0 + h2 * 16;
-            if (cq + 16 <= p.f) {
+            for (int j = 0; j < 8; ++j) w16[hh * 8 + j] = pack2(vl[2 * j], vl[2 * j + 1]);
+            if (!chunk_full && row < p.n) {         // chunk straddles f: scalar stores of the valid columns
+              __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) w16[j] = __float_as_uint(vl[h2 * 16 + j]);
-              store_rows64(stg, w16, reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(p.y) + row_w0 * p.ldy + cq),
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.f) yr[c0 + j] = __float2bfloat16_rn(vl[j]);
+            }
+          } else {
+            if (c0 + 16 <= p.f) {
+              uint32_t wf[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) wf[j] = __float_as_uint(vl[j]);
+              store_rows64(stg, wf, reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(p.y) + row_w0 * p.ldy + c0),
                            p.ldy * 4, rows_ok, lane);
             } else if (row < p.n) {
               float* yr = reinterpret_cast<float*>(p.y) + row * p.ldy;
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (cq + j < p.f) yr[cq + j] = vl[h2 * 16 + j];
+                if (c0 + j < p.f) yr[c0 + j] = vl[j];
             }
           }
         }
+        if (p.y_bf16 && chunk_full)
+          store_rows64(stg, w16, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.y) + row_w0 * p.ldy + c_lo + cc * 32),
+                       p.ldy * 2, rows_ok, lane);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -500,7 +487,7 @@ extern "C" int acm_fused_agg_fwd(const void* z, const void* d, const void* x, in
   using namespace acm;
   using namespace acm::fused;
   if (fp != FP) { set_error("fused_agg_fwd: built for a padded out_features of %d (got %d)", FP, fp); return ACM_ERR_UNSUPPORTED; }
-  ACM_CHECK_ARG(z && d && x && wcat_t && pack && y && att, "fused_agg_fwd: null pointer");
+  ACM_CHECK_ARG(z && d && x && wcat_t && pack && y && att && h_i, "fused_agg_fwd: null pointer (h_i is required: the epilogue reads HI back from it)");
   ACM_CHECK_ARG(k >= 8 && k <= 256 && k % 8 == 0 && ldx >= k && ldw >= k, "fused_agg_fwd: need 8 <= k <= 256, k %% 8 == 0, ldx, ldw >= k");
   ACM_CHECK_ARG(f >= 1 && f <= fp, "fused_agg_fwd: need 1 <= f <= fp");
   ACM_CHECK_ARG(y_dtype == ACM_F32 || y_dtype == ACM_BF16, "fused_agg_fwd: bad y dtype %d", y_dtype);
@@ -521,7 +508,7 @@ extern "C" int acm_fused_agg_fwd(const void* z, const void* d, const void* x, in
   if ((rc = make_map(&md, d, (uint64_t)k, (uint64_t)n_rows, (uint64_t)ldx, BK, BM, "D"))) return rc;
   if ((rc = make_map(&mx, x, (uint64_t)k, (uint64_t)n_rows, (uint64_t)ldx, BK, BM, "X"))) return rc;
   if ((rc = make_map(&mw, wcat_t, (uint64_t)k, (uint64_t)(3 * FP), (uint64_t)ldw, BK, FP, "Wcat^T"))) return rc;
-  const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kStgBytes + 3 * FP * 4 + 64 + 2 * 2 * BM * 16 + 128 + 1024;
+  const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kStgBytes + 3 * FP * 4 + 64 + 2 * kParts * BM * 16 + 128 + 1024;
   cudaError_t e = cudaFuncSetAttribute(fused_agg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("fused_agg_fwd: smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e)); return (int)e; }
   int sms = 148, dev = 0;

@@ -32,7 +32,8 @@ struct BwdParams {
   const float* sig;
   const float* pack;
   int k, ln, variant, f, vec_g, g_bf16, ring;
-  int gtab;           // table_mode 1: t_lh rows are  T g[FP] | float {c att_L, c att_H, dz_L, dz_H}  (spmm_t_rank1_kernel)
+  int gtab;           // table_mode 1: t_lh = T g[table_rows][FP] then float4 {c att_L, c att_H, dz_L, dz_H}[table_rows]
+  int64_t table_rows; //   (spmm_t_rank1_kernel)
   float out_scale;
   void* t_lh;
   void* dh_all;
@@ -353,31 +354,31 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
     }
     if (p.gtab) {
       // rank-structured table (variant 1, no LayerNorm): the G row + four scalars instead of [dO_L | dO_H]
-      constexpr int TWG = FP + 16 / (int)sizeof(T);
       if (valid) {
         const float4 sc = make_float4(c * al[0], c * al[1], dz[0], dz[1]);
+        const int64_t scal_off = p.table_rows * FP * (int64_t)sizeof(T);   // byte offset of the scalar region
         if (p.peers.n > 0) {
-          const int64_t off = (p.peers.row_off + row) * TWG;
+          const int64_t grow = p.peers.row_off + row;
           if (p.peers.mc) {
             uint4 pk[sizeof(T) == 2 ? 1 : 2];
             Slice8<T>::store(reinterpret_cast<T*>(pk), G);
 #pragma unroll
             for (int h = 0; h < (int)(sizeof(pk) / 16); ++h)
-              multimem_st16(reinterpret_cast<char*>(p.peers.mc) + (off + f0) * (int64_t)sizeof(T) + h * 16, pk[h]);
-            if (gl == 0) multimem_st16(reinterpret_cast<char*>(p.peers.mc) + (off + FP) * (int64_t)sizeof(T),
+              multimem_st16(reinterpret_cast<char*>(p.peers.mc) + (grow * FP + f0) * (int64_t)sizeof(T) + h * 16, pk[h]);
+            if (gl == 0) multimem_st16(reinterpret_cast<char*>(p.peers.mc) + scal_off + grow * 16,
                                        make_uint4(__float_as_uint(sc.x), __float_as_uint(sc.y), __float_as_uint(sc.z), __float_as_uint(sc.w)));
           } else {
 #pragma unroll 1
             for (int r = 0; r < p.peers.n; ++r) {
-              T* dst = reinterpret_cast<T*>(p.peers.tables[r]) + off;
-              Slice8<T>::store(dst + f0, G);
-              if (gl == 0) *reinterpret_cast<float4*>(dst + FP) = sc;
+              char* tb = reinterpret_cast<char*>(p.peers.tables[r]);
+              Slice8<T>::store(reinterpret_cast<T*>(tb) + grow * FP + f0, G);
+              if (gl == 0) *reinterpret_cast<float4*>(tb + scal_off + grow * 16) = sc;
             }
           }
         } else {
-          T* dst = reinterpret_cast<T*>(p.t_lh) + row * TWG;
-          Slice8<T>::store(dst + f0, G);
-          if (gl == 0) *reinterpret_cast<float4*>(dst + FP) = sc;
+          char* tb = reinterpret_cast<char*>(p.t_lh);
+          Slice8<T>::store(reinterpret_cast<T*>(tb) + row * FP + f0, G);
+          if (gl == 0) *reinterpret_cast<float4*>(tb + scal_off + row * 16) = sc;
         }
       }
     } else if (p.peers.n > 0 && LANES < 32) {
@@ -539,7 +540,7 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
                            const void* g, int g_dtype, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
                            const float* att, const float* sig, const float* pack,
                            int k_channels, int ln_live, int variant, float out_scale,
-                           void* t_lh, int table_mode, void* dh_all, void* dos_pre, float* dpack,
+                           void* t_lh, int table_mode, int64_t table_rows, void* dh_all, void* dos_pre, float* dpack,
                            void* const* peer_tables, int n_peers, int64_t peer_row_off, void* multicast_table,
                            void* stream) {
   using namespace acm;
@@ -557,7 +558,8 @@ extern "C" int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
   p.pack = pack; p.k = k_channels; p.ln = ln_live; p.variant = variant; p.f = f; p.out_scale = out_scale;
   ACM_CHECK_ARG(table_mode == 0 || (table_mode == 1 && variant && !ln_live && fp >= 64),
                 "mix_bwd: table_mode 1 (rank-structured table) needs variant 1 without LayerNorm and fp >= 64");
-  p.t_lh = t_lh; p.dh_all = dh_all; p.dos_pre = dos_pre; p.dpack = dpack; p.gtab = table_mode;
+  ACM_CHECK_ARG(table_mode == 0 || table_rows >= peer_row_off + n_rows, "mix_bwd: table_rows must cover the rows written");
+  p.t_lh = t_lh; p.dh_all = dh_all; p.dos_pre = dos_pre; p.dpack = dpack; p.gtab = table_mode; p.table_rows = table_rows;
   p.peers = PeerTables{};
   p.peers.n = n_peers; p.peers.row_off = peer_row_off; p.peers.mc = n_peers > 0 ? multicast_table : nullptr;
   for (int r = 0; r < n_peers; ++r) p.peers.tables[r] = peer_tables[r];

@@ -118,63 +118,64 @@ spmm_t_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, 
 // so   (A^T dO_k)[i,:] = sum_j w_ji (c att_k[j]) G[j,:]  +  (sum_j w_ji dz_k[j]) a_k^T :
 // ONE gather of the G row (F wide) plus four scalars per stored edge serves BOTH channels -- half the
 // bytes of gathering [dO_L | dO_H] (2F wide), and half the exchange under a row partition.
-// Table row (written by mix_bwd in table_mode 1): T g[FP] | float {c att_L, c att_H, dz_L, dz_H}.
+// Table (written by mix_bwd in table_mode 1), one allocation of table_rows * (FP*sizeof(T) + 16) bytes:
+//     T g[table_rows][FP]   followed by   float4 {c att_L, c att_H, dz_L, dz_H}[table_rows]
+// (the G rows keep their natural 512-byte / 1-KB alignment: a first layout that appended the scalars to each
+// row -- 528-byte rows straddling DRAM pages and 128-byte lines -- ran at a third of the HBM peak).
+//
+// Gather = per-lane cp.async (LDGSTS) ring in shared memory, kRank1Stages neighbour rows in flight per lane, like
+// the fused forward kernel: a register-staged loop left the load scheduling to ptxas, which interleaved the loads
+// with the FMAs (two rows in flight, 50 % of the HBM peak measured).  Every lane copies its own 8-feature slice and
+// reads back only what it copied itself; the row's 16 bytes of scalars are copied by the first lane of the row's
+// lane group and broadcast by shuffle.
+constexpr int kRank1Stages = 8;
+template <typename T> struct Rank1Slot { static constexpr int kBytes = 8 * (int)sizeof(T) + 16; };
+
 template <typename T, int FP>
 __global__ void __launch_bounds__(kTWarps * 32)
 spmm_t_rank1_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                    const float* __restrict__ val, const T* __restrict__ table, const float* __restrict__ pack,
-                    const T* __restrict__ ptab, T* __restrict__ dh_all) {
+                    const float* __restrict__ val, const T* __restrict__ table, const float4* __restrict__ scal,
+                    const float* __restrict__ pack, const T* __restrict__ ptab, T* __restrict__ dh_all) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
-  constexpr int TWG = FP + 16 / (int)sizeof(T);       // row stride of the rank-1 table in elements
-  constexpr int U = 8;
+  constexpr int ST = kRank1Stages;
+  constexpr int SB = 8 * (int)sizeof(T);              // bytes of one 8-feature slice
+  constexpr int SLOT = Rank1Slot<T>::kBytes;
+  constexpr int STAGE = 32 * SLOT;                    // per warp and stage
+  extern __shared__ __align__(16) uint8_t rank1_ring[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LANES, gl = lane % LANES;
   const int64_t row = ((int64_t)blockIdx.x * kTWarps + warp) * RPW + sub;
-  if (row >= n_rows) return;
-  int64_t e = __ldg(rowptr + row);
-  const int64_t e1 = __ldg(rowptr + row + 1);
-  const T* tab = table + gl * 8;
+  if (row >= n_rows) return;                          // whole lane groups leave together
+  const unsigned gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (sub * LANES));
+  const int64_t e = __ldg(rowptr + row);
+  const int n_e = (int)(__ldg(rowptr + row + 1) - e);
   float accL[8], accH[8], sL = 0.f, sH = 0.f;
 #pragma unroll
   for (int t = 0; t < 8; ++t) accL[t] = accH[t] = 0.f;
-  for (; e + U <= e1; e += U) {
-    int32_t c[U];
-    float w[U];
+  uint8_t* ring = rank1_ring + warp * (ST * STAGE) + lane * SLOT;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      c[u] = __ldg(col + e + u);
-      w[u] = val ? __ldg(val + e + u) : 1.f;
+  for (int st = 0; st < ST; ++st) {
+    if (st < n_e) {
+      const int64_t c = __ldg(col + e + st);
+      cp_async_slice<T>(ring_u32 + st * STAGE, table + c * FP + gl * 8);
+      if (gl == 0) cp_async16(ring_u32 + st * STAGE + SB, scal + c);
     }
-    Slice8<T> v[U];
-    float4 sc[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const T* r = table + (int64_t)c[u] * TWG;
-      v[u].load(r + gl * 8);
-      sc[u] = __ldg(reinterpret_cast<const float4*>(r + FP));
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float f[8];
-      v[u].to_float(f);
-      const float wl = w[u] * sc[u].x, wh = w[u] * sc[u].y;
-      sL = fmaf(w[u], sc[u].z, sL);
-      sH = fmaf(w[u], sc[u].w, sH);
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        accL[t] = fmaf(wl, f[t], accL[t]);
-        accH[t] = fmaf(wh, f[t], accH[t]);
-      }
-    }
+    cp_async_commit();
   }
-  for (; e < e1; ++e) {
-    const int32_t c = __ldg(col + e);
-    const float w = val ? __ldg(val + e) : 1.f;
-    const T* r = table + (int64_t)c * TWG;
+  for (int i = 0; i < n_e; ++i) {
+    cp_async_wait<ST - 1>();                          // the oldest group (edge i) has landed
+    const float w = val ? __ldg(val + e + i) : 1.f;
+    const int slot = i & (ST - 1);
     Slice8<T> v;
-    v.load(r + gl * 8);
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(r + FP));
+    v.load_plain(reinterpret_cast<const T*>(ring + slot * STAGE));
+    float4 sc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gl == 0) sc = *reinterpret_cast<const float4*>(ring + slot * STAGE + SB);
+    sc.x = __shfl_sync(gmask, sc.x, sub * LANES);
+    sc.y = __shfl_sync(gmask, sc.y, sub * LANES);
+    sc.z = __shfl_sync(gmask, sc.z, sub * LANES);
+    sc.w = __shfl_sync(gmask, sc.w, sub * LANES);
     float f[8];
     v.to_float(f);
     const float wl = w * sc.x, wh = w * sc.y;
@@ -185,15 +186,20 @@ spmm_t_rank1_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ ro
       accL[t] = fmaf(wl, f[t], accL[t]);
       accH[t] = fmaf(wh, f[t], accH[t]);
     }
+    if (i + ST < n_e) {
+      const int64_t c = __ldg(col + e + i + ST);
+      cp_async_slice<T>(ring_u32 + slot * STAGE, table + c * FP + gl * 8);
+      if (gl == 0) cp_async16(ring_u32 + slot * STAGE + SB, scal + c);
+    }
+    cp_async_commit();
   }
   // own row: dO_H[i,:] = c att_H[i] G[i,:] + dz_H[i] a_H
   float g[8], aL[8], aH[8];
   {
-    const T* r = table + (row0 + row) * TWG;
     Slice8<T> s;
-    s.load(r + gl * 8);
+    s.load(table + (row0 + row) * FP + gl * 8);
     s.to_float(g);
-    const float4 sc = __ldg(reinterpret_cast<const float4*>(r + FP));
+    const float4 sc = __ldg(scal + row0 + row);
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       aL[t] = __ldg(pack + pack_off_a(FP, 0) + gl * 8 + t);
@@ -502,12 +508,15 @@ extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
 
 extern "C" int acm_spmm_t_bwd_rank1(int dtype, int fp, int64_t n_rows, int64_t row0,
                                     const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
-                                    const void* g_table, const float* pack, const void* p_table, void* dh_all,
-                                    void* stream) {
+                                    const void* g_table, int64_t table_rows, const float* pack, const void* p_table,
+                                    void* dh_all, void* stream) {
   using namespace acm;
   ACM_CHECK_ARG(dtype == ACM_F32 || dtype == ACM_BF16, "spmm_t_bwd_rank1: bad dtype %d", dtype);
   ACM_CHECK_ARG(rowptr_t && col_t && g_table && pack && dh_all, "spmm_t_bwd_rank1: null pointer");
   ACM_CHECK_ARG(fp >= 64, "spmm_t_bwd_rank1: built for padded widths >= 64 (got %d)", fp);
+  ACM_CHECK_ARG(table_rows >= row0 + n_rows, "spmm_t_bwd_rank1: table_rows must cover the own rows");
+  const size_t el = dtype == ACM_BF16 ? 2 : 4;
+  const float4* scal = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(g_table) + (size_t)table_rows * fp * el);
   if (n_rows == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 #define ACM_R_LAUNCH(TT)                                                                           \
@@ -521,8 +530,13 @@ extern "C" int acm_spmm_t_bwd_rank1(int dtype, int fp, int64_t n_rows, int64_t r
     constexpr int RPB = (32 / (FP / 8)) * kTWarps;                                                 \
     const int64_t blocks = (n_rows + RPB - 1) / RPB;                                               \
     ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_t_bwd_rank1: too many rows");                        \
-    spmm_t_rank1_kernel<TT, FP><<<(unsigned)blocks, kTWarps * 32, 0, st>>>(                        \
-        n_rows, row0, rowptr_t, col_t, val_t, (const TT*)g_table, pack, (const TT*)p_table, (TT*)dh_all);
+    constexpr size_t smem = (size_t)kTWarps * kRank1Stages * 32 * Rank1Slot<TT>::kBytes;           \
+    if (smem > 48 * 1024) {                                                                        \
+      cudaError_t e_ = cudaFuncSetAttribute(spmm_t_rank1_kernel<TT, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e_ != cudaSuccess) { set_error("spmm_t_bwd_rank1: smem attribute: %s", cudaGetErrorString(e_)); return (int)e_; } \
+    }                                                                                              \
+    spmm_t_rank1_kernel<TT, FP><<<(unsigned)blocks, kTWarps * 32, smem, st>>>(                     \
+        n_rows, row0, rowptr_t, col_t, val_t, (const TT*)g_table, scal, pack, (const TT*)p_table, (TT*)dh_all);
   if (dtype == ACM_BF16) { ACM_R_LAUNCH(__nv_bfloat16) } else { ACM_R_LAUNCH(float) }
 #undef ACM_R_BODY
 #undef ACM_R_LAUNCH

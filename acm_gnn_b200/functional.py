@@ -128,12 +128,20 @@ def use_rank1_table(cfg: LayerConfig, op, fp: int) -> bool:
     exchanges) the G row plus four scalars per node instead of the 2*out_features wide [dO_L|dO_H] row --
     half the bytes (csrc/spmm_t.cu spmm_t_rank1_kernel).  Wide rows only (padded width >= 64) and only when
     the transposed operator has no long rows (those keep the segment-parallel pass of the plain table).
-    ``ACMB200_BWD_RANK1=off`` keeps the [dO_L|dO_H] table."""
-    return (bool(cfg.variant) and not cfg.ln_live and fp >= 64 and op.low.long_rows(True) is None
-            and _knob("ACMB200_BWD_RANK1"))
+    ``ACMB200_BWD_RANK1`` = auto (default): under a row partition only -- there it halves the NVLink exchange;
+    on one GPU the rank-1 gather issues twice the instructions per byte (18 FMAs + the scalar broadcast per
+    512-byte row) and measured 38.5 ms against 35 ms for the plain table at the headline size; on: always; off."""
+    v = os.environ.get("ACMB200_BWD_RANK1", "auto").lower()
+    if v in ("off", "0"):
+        return False
+    if v not in ("auto", "on", "1"):
+        raise ValueError(f"ACMB200_BWD_RANK1={v!r}: expected auto, on or off")
+    if v == "auto" and cfg.dist is None:
+        return False
+    return bool(cfg.variant) and not cfg.ln_live and fp >= 64 and op.low.long_rows(True) is None
 
 
-FUSED_FWD_DEFAULT = "off"     # opt-in until it beats the unfused launches (profiles/: 11.7 vs 10.5 ms at the headline size)
+FUSED_FWD_DEFAULT = "auto"
 
 
 def use_fused_forward(cfg: LayerConfig, impl: int, fp: int, f: int, k_channels: int, ldx: int) -> bool:
@@ -478,7 +486,7 @@ class AcmLayerFunction(torch.autograd.Function):
             # stay in TMEM, [S_L|S_H] and HI are written once (bf16) for the backward -- or not at all
             _lib.call("acm_fused_agg_fwd", z.data_ptr(), d.data_ptr(), xs.data_ptr(), ldx, wt.data_ptr(), ldx, pack.data_ptr(),
                       n, ldx, f, fp, float(cfg.out_scale), y.data_ptr(), _lib.ACM_BF16 if y_bf16 else _lib.ACM_F32, f,
-                      h_lh.data_ptr() if need_grad else 0, h_i.data_ptr() if need_grad else 0, att.data_ptr(), _lib.ptr(sig),
+                      h_lh.data_ptr() if need_grad else 0, h_i.data_ptr(), att.data_ptr(), _lib.ptr(sig),
                       st, tag=fp)
         else:
             _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, row0, csr[0], csr[1], csr[2], 0,
@@ -524,14 +532,15 @@ class AcmLayerFunction(torch.autograd.Function):
         dpack = torch.zeros(12 * fp + 16, dtype=torch.float32, device=dev)
         needs_t = not (ctx.agg_first or ctx.bwd_input)      # a transposed aggregation follows
         rank1 = needs_t and use_rank1_table(cfg, op, fp)
-        tw = (fp + (8 if cfg.dtype == "bf16" else 4)) if rank1 else 2 * fp     # table row width in elements
+        tw = (fp + (8 if cfg.dtype == "bf16" else 4)) if rank1 else 2 * fp     # table bytes per row / element size
+        t_rows = n if cfg.dist is None else cfg.dist.world * cfg.dist.rows_per_rank
         push = (cfg.dist is not None and needs_t and cfg.dist.push_enabled())
         if push:
             # fused mix_bwd + all-gather of the backward operand table (peer stores over NVLink)
             t_table, hdl, ptrs, mc = cfg.dist.symm_table((cfg.layer_key, "bwd"), tw, tdt, dev)
             _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), gdt, f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
                       att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
-                      float(cfg.out_scale), 0, int(rank1), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
+                      float(cfg.out_scale), 0, int(rank1), t_rows, dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
                       ctypes.addressof(ptrs), cfg.dist.world, op.row0, mc, st, tag=fp)
             hdl.barrier(channel=0)
             t_lh = None
@@ -539,7 +548,7 @@ class AcmLayerFunction(torch.autograd.Function):
             t_lh = torch.empty(n, tw, dtype=tdt, device=dev)
             _lib.call("acm_mix_bwd", cdt, fp, f, n, g.data_ptr(), gdt, f, o_save.data_ptr(), h_i.data_ptr(), _lib.ptr(o_s),
                       att.data_ptr(), sig.data_ptr(), pack.data_ptr(), K, int(cfg.ln_live), int(cfg.variant),
-                      float(cfg.out_scale), t_lh.data_ptr(), int(rank1), dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
+                      float(cfg.out_scale), t_lh.data_ptr(), int(rank1), n, dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
                       0, 0, 0, 0, st, tag=fp)
 
         dwcat = torch.zeros(fin, 3 * fp, dtype=torch.float32, device=dev)
@@ -558,11 +567,23 @@ class AcmLayerFunction(torch.autograd.Function):
                           dwcat[:, k * fp:].data_ptr(), 3 * fp, n, fin, fp, st, tag=fp)
         else:
             if not push:
-                t_table = t_lh if cfg.dist is None else cfg.dist.all_gather_rows(t_lh)
+                if cfg.dist is None:
+                    t_table = t_lh
+                elif rank1:
+                    # NCCL path: the rank-1 table is two regions (G rows, then the scalars) -> gather each
+                    flat = t_lh.view(-1)
+                    g_all = cfg.dist.all_gather_rows(flat[:n * fp].view(n, fp))
+                    s_all = cfg.dist.all_gather_rows(flat[n * fp:].view(n, tw - fp))
+                    t_table = torch.empty(g_all.shape[0], tw, dtype=tdt, device=dev)
+                    t_table.view(-1)[:g_all.numel()].copy_(g_all.view(-1))
+                    t_table.view(-1)[g_all.numel():].copy_(s_all.view(-1))
+                    del flat, g_all, s_all
+                else:
+                    t_table = cfg.dist.all_gather_rows(t_lh)
             if rank1:
                 _lib.call("acm_spmm_t_bwd_rank1", cdt, fp, n, op.row0, op.low.rowptr_t.data_ptr(), op.low.col_t.data_ptr(),
-                          op.low.val_t.data_ptr(), t_table.data_ptr(), pack.data_ptr(), _lib.ptr(p_tab), dh_all.data_ptr(),
-                          st, tag=fp)
+                          op.low.val_t.data_ptr(), t_table.data_ptr(), t_table.shape[0], pack.data_ptr(), _lib.ptr(p_tab),
+                          dh_all.data_ptr(), st, tag=fp)
                 lr = None
             else:
                 lr = _long_pass(op.low, True, t_table, fp, 2, cdt, st)

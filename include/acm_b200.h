@@ -157,8 +157,9 @@ int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row0,
  * replacing torch.mm x3 + relu + attention3 + the mix of layers.py:163-165,188-204,94-119 without the
  * [S_L|S_H|HI] round trip through HBM.  z, d, x: bf16 [n_rows, ldx] (k = padded input width, multiple
  * of 8, <= 256); wcat_t: bf16 [3*fp, ldw] K-major (acm_pack_params); pack: value pack.  Outputs: y
- * (fp32 or bf16, row stride ldy), att [n_rows,3]; for the backward (may be NULL for inference):
- * s_lh bf16 [n_rows, 2*fp] = pre-relu [S_L|S_H], h_i bf16 [n_rows, fp], sig [n_rows,3].
+ * (fp32 or bf16, row stride ldy), att [n_rows,3], h_i bf16 [n_rows, fp] (pre-relu HI; required, the
+ * epilogue reads it back); for the backward only (may be NULL for inference): s_lh bf16 [n_rows, 2*fp] =
+ * pre-relu [S_L|S_H], sig [n_rows,3].
  * 3 channels, no LayerNorm, variant 0 only; returns ACM_ERR_UNSUPPORTED for fp != 256. */
 int acm_fused_agg_fwd(const void* z, const void* d, const void* x, int64_t ldx,
                       const void* wcat_t, int64_t ldw, const float* pack,
@@ -226,13 +227,14 @@ int acm_set_gather_mode(int mode);
  * aggregate-first order passes its [S_L|S_H] table and saves no second copy); variant 1 -> [O_L|O_H].
  * table_mode 0: t_lh rows are [dS_L | dS_H] (2*fp wide).  table_mode 1 (variant 1 without LayerNorm,
  * fp >= 64): the rank-structured table of acm_spmm_t_bwd_rank1 -- with the relu before the aggregation
- * dO_k = c att_k G + dz_k a_k^T, so a row is  T g[fp] | float {c att_L, c att_H, dz_L, dz_H}
- * (row stride fp + 16/sizeof(T) elements): half the bytes to gather and to exchange. */
+ * dO_k = c att_k G + dz_k a_k^T, so the table is  T g[table_rows][fp]  followed by
+ * float4 {c att_L, c att_H, dz_L, dz_H}[table_rows]  (one allocation of table_rows*(fp*sizeof(T)+16) bytes;
+ * row r of this call is written at index peer_row_off + r): half the bytes to gather and to exchange. */
 int acm_mix_bwd(int dtype, int fp, int f, int64_t n_rows,
                 const void* g, int g_dtype, int64_t ldg, const void* o_lh, const void* h_i, const void* o_s,
                 const float* att, const float* sig, const float* pack,
                 int k_channels, int ln_live, int variant, float out_scale,
-                void* t_lh, int table_mode, void* dh_all, void* dos_pre, float* dpack,
+                void* t_lh, int table_mode, int64_t table_rows, void* dh_all, void* dos_pre, float* dpack,
                 void* const* peer_tables, int n_peers, int64_t peer_row_off, void* multicast_table, void* stream);
 
 /* Transposed aggregation (autograd of torch.spmm(adj_low,.) / torch.spmm(adj_high,.)):
@@ -254,7 +256,8 @@ int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
  * caller uses acm_spmm_t_bwd when the transposed operator has rows with more than 256 edges. */
 int acm_spmm_t_bwd_rank1(int dtype, int fp, int64_t n_rows, int64_t row0,
                          const int64_t* rowptr_t, const int32_t* col_t, const float* val_t,
-                         const void* g_table, const float* pack, const void* p_table, void* dh_all, void* stream);
+                         const void* g_table, int64_t table_rows, const float* pack, const void* p_table,
+                         void* dh_all, void* stream);
 
 /* Plain single-table aggregation out = [relu](A . table), table T [*, fp]; used for the
  * structure channel relu(mm(adj_low_unnormalized, struc_low)) (layers.py:207-209) and its

@@ -39,8 +39,11 @@ def main():
              ("bf16", False, 4100, True, 0, 256, NS), ("fp32", False, 5003, False, 0, 64, NS),
              ("bf16", True, 4100, True, 0, 256, NS), ("bf16", False, 4100, False, 0, 256, NS),
              ("bf16", True, 4100, False, 0, 256, OLD), ("fp32", False, 5003, False, 0, 64, dict(OLD, **NS)),
-             ("bf16", False, 4100, True, 0, 256, dict(OLD, **NS)), ("bf16", True, 3001, False, 1, 64, OLD)]
-    knobs = ("ACMB200_LOCAL_TABLE", "ACMB200_BWD_INPUT", "ACMB200_REORDER")
+             ("bf16", False, 4100, True, 0, 256, dict(OLD, **NS)), ("bf16", True, 3001, False, 1, 64, OLD),
+             # rank-structured backward table (variant 1: G row + 4 scalars exchanged instead of [dO_L|dO_H]) is the
+             # default under a partition; these keep the plain 2F-wide table push covered
+             ("bf16", True, 4100, False, 0, 256, {"ACMB200_BWD_RANK1": "off"}), ("fp32", True, 4096, False, 0, 64, {"ACMB200_BWD_RANK1": "off"})]
+    knobs = ("ACMB200_LOCAL_TABLE", "ACMB200_BWD_INPUT", "ACMB200_REORDER", "ACMB200_BWD_RANK1")
     for mode, variant, n, staged, struct, hid, env in cases:
         for k in knobs:
             os.environ.pop(k, None)

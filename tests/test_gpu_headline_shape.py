@@ -17,11 +17,17 @@ Stated tolerances at this size:
                  ATen's blocked reductions -- measured 3e-7 .. 3e-4, and 1.2e-3 for the high-pass weight
                  gradient, whose summands (dS_H - A^T dS_H on smooth signals) cancel to ~1e-3 of their size;
                  the reference's own fp32 run is 2.7e-4 away from fp64 on that tensor;
-  bf16 storage : forward max err <= 3e-2 * max|ref| as everywhere; gradients relative Frobenius <= 2e-2
-                 and cosine >= 0.999 per tensor vs fp64 -- at 10^5 nodes the bf16 storage noise of the
-                 saved activations averages out in the parameter-gradient sums, unlike on the
-                 few-hundred-node golden graphs where 0.35 is the stated (and emulated,
-                 test_bf16_noise_cpu.py) bound.
+  bf16 storage : forward max err <= 3e-2 * max|ref| as everywhere.  Gradients: the round-1 review expected the
+                 bf16 storage noise to average out at 10^5 nodes (<= 2e-2); MEASURED it does not -- relative
+                 Frobenius 6e-2 .. 1.4e-1 (cosine 0.994 .. 0.9999), about the same as on the small golden
+                 graphs.  The reason is cancellation, not the kernels: with all-positive, row-normalised
+                 features and softmax-CE gradients that sum to ~0 over the nodes, dW = sum_i x_i (x) dh_i
+                 cancels to a few per cent of its summands, so the 2^-9 relative rounding of the STORED
+                 dh_i / S_i rows survives as a several-per-cent error of the sum, at any N.  The bound is
+                 therefore tied to an emulation: the fp32 oracle with the same storage points rounded to
+                 bf16 (tests/test_bf16_noise_cpu.py::_layer) run on THIS workload gives the noise level of
+                 bf16 storage itself; every GPU gradient must be within 4x that level (and <= 0.25 relative
+                 Frobenius, cosine >= 0.99).  Kernel logic is what the fp32 mode checks at 3e-3 above.
 """
 import os
 
@@ -34,7 +40,7 @@ from helpers import O
 pytestmark = pytest.mark.gpu
 
 N, E, FIN, HID, NCLS = 100_000, 2_000_000, 256, 256, 16
-BF16_FRO, BF16_COS = 2e-2, 0.999
+BF16_FRO, BF16_COS = 0.25, 0.99
 FP32_FRO = 3e-3
 
 
@@ -65,8 +71,20 @@ def workload():
                 "grads": {f"{grp}.{k}": t.grad.clone() for grp, d in ps.items() for k, t in d.items() if t.grad is not None}}
 
     ref, ref64 = run(torch.float32), run(torch.float64)
+
+    # noise level of bf16 STORAGE on this workload: fp32 oracle with the storage points rounded to bf16
+    from test_bf16_noise_cpu import _layer as q_layer
+    ps = {grp: {k: t.detach().clone() for k, t in d.items()} for grp, d in params.items()}
+    for grp in ps.values():
+        for k, t in grp.items():
+            if not k.startswith(("layer_norm", "struc", "att_struc")):
+                t.requires_grad_(True)
+    out_q = q_layer(ps["gcns.1"], torch.relu(q_layer(ps["gcns.0"], x, low, True)), low, True)
+    O.train_step_loss(out_q, labels, idx).backward()
+    noise = {f"{grp}.{k}": float((t.grad.double() - ref64["grads"][f"{grp}.{k}"]).norm() / ref64["grads"][f"{grp}.{k}"].norm())
+             for grp, d in ps.items() for k, t in d.items() if t.grad is not None}
     sd = {f"{grp}.{k}": t.detach().clone() for grp, d in params.items() for k, t in d.items()}
-    return dict(row=row, col=col, op_ref=op_ref, x=x, labels=labels, idx=idx, ref=ref, ref64=ref64, sd=sd)
+    return dict(row=row, col=col, op_ref=op_ref, x=x, labels=labels, idx=idx, ref=ref, ref64=ref64, sd=sd, noise=noise)
 
 
 def _rel(got, ref):
@@ -130,10 +148,11 @@ def test_headline_shape_matches_oracle(workload, mode, order, staged, monkeypatc
         if mode == "fp32":
             ok = fro <= max(4 * fro_ref, FP32_FRO)
         else:
-            ok = fro <= BF16_FRO and cos >= BF16_COS
+            ok = fro <= min(BF16_FRO, max(4 * w["noise"][k], 2e-2)) and cos >= BF16_COS
         if not ok:
             bad.append(k)
-    table = "; ".join(f"{k}: {v[0]:.2e} (cos {v[1]:.6f}, fp32 oracle {v[2]:.1e})" for k, v in sorted(report.items()))
+    table = "; ".join(f"{k}: {v[0]:.2e} (cos {v[1]:.6f}, fp32 oracle {v[2]:.1e}, bf16-storage emulation {w['noise'].get(k, float('nan')):.1e})"
+                      for k, v in sorted(report.items()))
     assert not bad, f"gradients out of tolerance ({mode}, order {order}, staged {staged}): {bad}\nrel.fro vs fp64 -- {table}"
     assert len(report) >= 14, sorted(report)
     worst = max(report.items(), key=lambda kv: kv[1][0])

@@ -410,7 +410,7 @@ def test_rank1_backward_table_matches_oracle(f, mode, monkeypatch):
     yo, _ = _oracle_layer(p, xo, op_ref, True)
     (yo * w).sum().backward()
     got = {}
-    for knob in ("auto", "off"):
+    for knob in ("on", "off"):
         monkeypatch.setenv("ACMB200_BWD_RANK1", knob)
         layer.zero_grad(set_to_none=True)
         xc = x.clone().cuda().requires_grad_(True)
@@ -423,14 +423,14 @@ def test_rank1_backward_table_matches_oracle(f, mode, monkeypatch):
         finally:
             _lib.set_timer(None)
         names = set(k.split(":")[0] for k in timer.spans)
-        assert ("acm_spmm_t_bwd_rank1" in names) == (knob == "auto") and ("acm_spmm_t_bwd" in names) == (knob == "off"), names
+        assert ("acm_spmm_t_bwd_rank1" in names) == (knob == "on") and ("acm_spmm_t_bwd" in names) == (knob == "off"), names
         _close(y, yo, mode, "y")
         _close_grad(xc.grad, xo.grad, mode, f"dx ({knob})")
         for k in ("weight_low", "weight_high", "weight_mlp", "att_vec_low", "att_vec_high", "att_vec_mlp", "att_vec"):
             _close_grad(getattr(layer, k).grad, p[k].grad, mode, f"d{k} ({knob})")
         got[knob] = (xc.grad.clone(), layer.weight_low.grad.clone(), layer.weight_high.grad.clone())
     if mode == "fp32":
-        for a, b in zip(got["auto"], got["off"]):
+        for a, b in zip(got["on"], got["off"]):
             assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
 
 
