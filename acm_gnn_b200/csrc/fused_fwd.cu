@@ -22,10 +22,12 @@
 //   bound -- 8 warps, 3.5 k dependent instructions each per tile, issue slots 20 % busy: 11.7 ms against
 //   10.5 ms for the unfused launches, profiles/r2d_*.  Sixteen epilogue warps hide those latencies.)
 //
-// Warps: 0 = TMA producer (3-stage ring of {A 128x64, B 256x64} bf16 tiles, 128B swizzle),
+// Warps: 0 = TMA producer (4-stage ring of {A 128x64, B 256x64} bf16 tiles, 128B swizzle),
 //        1 = MMA issuer + TMEM owner, 2..17 = epilogue (warp w: lane quadrant w & 3, column quarter (w-2) >> 2).
-// All global stores go through a per-warp transposition tile so that every store instruction writes
-// full 32-byte sectors of row-contiguous bytes.
+// Global stores: every thread writes 32-byte pieces of ITS OWN row with one 256-bit store (st.global.v8.b32,
+// SASS STG.E.256 -- new on sm_100): each store instruction fills 32 whole sectors, so no shared-memory
+// transposition tile is needed (the v2 kernel's tile cost ~450 instructions and 512 KB of shared-memory
+// traffic per CTA tile next to the 1.1 MB the TMA ring and the MMAs already move).
 #include <cuda.h>
 
 #include "acm_common.cuh"
@@ -37,7 +39,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
 constexpr int FP = 256;                   // out_features (padded): the only width this kernel is built for
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kParts = 4;                 // column parts per channel = epilogue warps per TMEM lane quadrant
 constexpr int kEpiWarps = 4 * kParts;
 constexpr int CW = FP / kParts;           // columns of every channel owned by one epilogue warp
@@ -45,8 +47,6 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = BM * BK * 2;           // 16 KB
 constexpr uint32_t kBBytes = FP * BK * 2;           // 32 KB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;
-constexpr int kStgStride = 80;                      // bytes per staging row: 64 payload + 16 pad (conflict free)
-constexpr int kStgBytes = 32 * kStgStride;          // per warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -145,31 +145,19 @@ struct Params {
   float* att; float* sig;
 };
 
-// one 32-row x 64-byte payload per call: lane r holds the 64 bytes (16 words) of tile row r; the
-// warp writes them to dst + row * ld_bytes (+ this chunk's byte offset, already applied to dst) as
-// row-contiguous 64-byte segments, 8 rows per store instruction.  rows_ok = number of valid rows.
-__device__ __forceinline__ void store_rows64(uint8_t* stg, const uint32_t (&w)[16], uint8_t* dst, int64_t ld_bytes,
-                                             int rows_ok, int lane) {
-  uint4* mine = reinterpret_cast<uint4*>(stg + lane * kStgStride);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) mine[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-  __syncwarp();
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int rr = it * 8 + (lane >> 2);
-    const int cc = (lane & 3) * 16;
-    if (rr < rows_ok) {
-      const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * kStgStride + cc);
-      *reinterpret_cast<uint4*>(dst + rr * ld_bytes + cc) = v;
-    }
-  }
-  __syncwarp();
+// 32 bytes of this thread's own row, one 256-bit access (dst / src 32-byte aligned)
+__device__ __forceinline__ void st_row32(void* dst, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void ld_row32(const void* src, uint32_t* w) {
+  asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(src) : "memory");
 }
 
-// sum_j relu(acc[row, j]) * a[j] over this warp's 128 columns of one channel (thread = row); the raw
-// (pre-relu) accumulator chunk goes to the backward's table on the way (tab = nullptr: inference)
-__device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, uint8_t* stg, __nv_bfloat16* tab, int64_t ld_bytes,
-                                         int rows_ok, int lane) {
+// sum_j relu(acc[row, j]) * a[j] over this warp's CW columns of one channel (thread = row); the raw (pre-relu)
+// accumulators go to `dst` (this thread's row of the backward's table, bf16; nullptr: not stored) on the way
+__device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, __nv_bfloat16* dst) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent FMA chains
 #pragma unroll
   for (int cc = 0; cc < CW / 32; ++cc) {
@@ -183,11 +171,12 @@ __device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, uint8_t
       a2 = fmaf(fmaxf(v[j + 2], 0.f), av.z, a2);
       a3 = fmaf(fmaxf(v[j + 3], 0.f), av.w, a3);
     }
-    if (tab) {
+    if (dst) {
       uint32_t w16[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) w16[j] = pack2(v[2 * j], v[2 * j + 1]);
-      store_rows64(stg, w16, reinterpret_cast<uint8_t*>(tab + cc * 32), ld_bytes, rows_ok, lane);
+      st_row32(dst + cc * 32, w16);
+      st_row32(dst + cc * 32 + 16, w16 + 8);
     }
   }
   return (a0 + a1) + (a2 + a3);
@@ -199,9 +188,8 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  // ring | staging | a_k [3][256] f32 | avec [16] f32 | z exchange [2][kParts][128][4] f32 | barriers
-  const uint32_t off_stg = kStages * kStageBytes;
-  const uint32_t off_a = off_stg + kEpiWarps * kStgBytes;
+  // ring | a_k [3][256] f32 | avec [16] f32 | z exchange [2][kParts][128][4] f32 | barriers
+  const uint32_t off_a = kStages * kStageBytes;
   const uint32_t off_avec = off_a + 3 * FP * 4;
   const uint32_t off_z = off_avec + 64;
   const uint32_t off_bar = off_z + 2 * kParts * BM * 16;
@@ -304,35 +292,35 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     const int q = warp & 3;
     const int part = (warp - 2) >> 2;
     const int c_lo = part * CW;
-    uint8_t* stg = gbase + off_stg + (warp - 2) * kStgBytes;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const float inv_k = 1.f / 3.f;
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++t) {
       const uint32_t tp = (uint32_t)(t & 1);
-      const int64_t row_w0 = tile * BM + q * 32;          // first row of this warp
-      const int64_t row = row_w0 + lane;
-      int rows_ok = (int)((p.n - row_w0) < 32 ? (p.n - row_w0) : 32);
-      if (rows_ok < 0) rows_ok = 0;
+      const int64_t row = tile * BM + q * 32 + lane;
+      const bool row_ok = row < p.n;
 
       // ---- HI: R0 -> h_i (bf16), identity logit
       mbar_wait(bar_acc + 0, tp);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const float zI = row_dot(lane_addr + (uint32_t)c_lo, s_a + 2 * FP + c_lo, stg, p.h_i + row_w0 * FP + c_lo,
-                               (int64_t)FP * 2, rows_ok, lane);
+      __nv_bfloat16* hrow = p.h_i + (row_ok ? row : 0) * FP + c_lo;
+      const float zI = row_dot(lane_addr + (uint32_t)c_lo, s_a + 2 * FP + c_lo, row_ok ? hrow : nullptr);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_r0);
 
       // ---- logits of S_L (R1) while S_H is being accumulated, then of S_H (R0); raw accumulators -> table
+      __nv_bfloat16* trow = (p.s_lh && row_ok) ? p.s_lh + row * (2 * FP) + c_lo : nullptr;
       mbar_wait(bar_acc + 8, tp);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const float zL = row_dot(lane_addr + (uint32_t)(FP + c_lo), s_a + c_lo, stg,
-                               p.s_lh ? p.s_lh + row_w0 * (2 * FP) + c_lo : nullptr, (int64_t)FP * 4, rows_ok, lane);
+      const float zL = row_dot(lane_addr + (uint32_t)(FP + c_lo), s_a + c_lo, trow);
+      // this thread's HI values for the second pass: issued now, consumed after the S_H pass (L2 latency hidden)
+      uint32_t hi[CW / 2];
+#pragma unroll
+      for (int j = 0; j < CW / 16; ++j) ld_row32(hrow + j * 16, hi + j * 8);
       mbar_wait(bar_acc + 16, tp);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const float zH = row_dot(lane_addr + (uint32_t)c_lo, s_a + FP + c_lo, stg,
-                               p.s_lh ? p.s_lh + row_w0 * (2 * FP) + FP + c_lo : nullptr, (int64_t)FP * 4, rows_ok, lane);
+      const float zH = row_dot(lane_addr + (uint32_t)c_lo, s_a + FP + c_lo, trow ? trow + FP : nullptr);
 
       // ---- combine the column parts (fixed order: identical sums in every warp of the quadrant), attention
       *reinterpret_cast<float4*>(s_z + ((tp * kParts + part) * BM + q * 32 + lane) * 4) = make_float4(zL, zH, zI, 0.f);
@@ -367,7 +355,7 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       const float rden = __fdividef(1.f, den);
 #pragma unroll
       for (int k = 0; k < 3; ++k) al[k] *= rden;
-      if (row < p.n && part < 2) {
+      if (row_ok && part < 2) {
         float* dst = part == 0 ? p.att : p.sig;
         if (dst) {
           dst[row * 3 + 0] = part == 0 ? al[0] : sgm[0];
@@ -377,57 +365,41 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       }
       const float cL = p.out_scale * al[0], cH = p.out_scale * al[1], cI = p.out_scale * al[2];
 
-      // ---- second pass: Y = c (att_L relu(S_L) + att_H relu(S_H) + att_I relu(HI)), 16 columns at a time;
-      // HI comes back from the h_i rows this warp stored above (same warp, __syncwarp in store_rows64)
-      const __nv_bfloat16* hrow = p.h_i + (row < p.n ? row : 0) * FP;
+      // ---- second pass: Y = c (att_L relu(S_L) + att_H relu(S_H) + att_I relu(HI)), 16 columns at a time
+      // (columns >= f are padding with zero weights and are never stored; f % 16 == 0 for bf16 Y, % 8 for fp32)
 #pragma unroll
-      for (int cc = 0; cc < CW / 32; ++cc) {
-        uint32_t w16[16];
-        const bool chunk_full = c_lo + cc * 32 + 32 <= p.f;
+      for (int hc = 0; hc < CW / 16; ++hc) {
+        const int c0 = c_lo + hc * 16;
+        float vl[16], vh[16];
+        tmem_ld16_issue(lane_addr + (uint32_t)(FP + c0), vl);
+        tmem_ld16_issue(lane_addr + (uint32_t)c0, vh);
+        tmem_wait_ld();
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int c0 = c_lo + cc * 32 + hh * 16;
-          const uint4 h0 = __ldcg(reinterpret_cast<const uint4*>(hrow + c0));
-          const uint4 h1 = __ldcg(reinterpret_cast<const uint4*>(hrow + c0 + 8));
-          float vl[16], vh[16];
-          tmem_ld16_issue(lane_addr + (uint32_t)(FP + c0), vl);
-          tmem_ld16_issue(lane_addr + (uint32_t)c0, vh);
-          tmem_wait_ld();
-          const uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 h2 = unpack2(hw[j]);
-            vl[2 * j] = fmaf(cL, fmaxf(vl[2 * j], 0.f), fmaf(cH, fmaxf(vh[2 * j], 0.f), cI * fmaxf(h2.x, 0.f)));
-            vl[2 * j + 1] = fmaf(cL, fmaxf(vl[2 * j + 1], 0.f), fmaf(cH, fmaxf(vh[2 * j + 1], 0.f), cI * fmaxf(h2.y, 0.f)));
-          }
-          // columns >= f are padding (zero weights): never stored
+        for (int j = 0; j < 8; ++j) {
+          const float2 h2 = unpack2(hi[hc * 8 + j]);
+          vl[2 * j] = fmaf(cL, fmaxf(vl[2 * j], 0.f), fmaf(cH, fmaxf(vh[2 * j], 0.f), cI * fmaxf(h2.x, 0.f)));
+          vl[2 * j + 1] = fmaf(cL, fmaxf(vl[2 * j + 1], 0.f), fmaf(cH, fmaxf(vh[2 * j + 1], 0.f), cI * fmaxf(h2.y, 0.f)));
+        }
+        if (row_ok) {
           if (p.y_bf16) {
+            if (c0 < p.f) {
+              uint32_t w8[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) w16[hh * 8 + j] = pack2(vl[2 * j], vl[2 * j + 1]);
-            if (!chunk_full && row < p.n) {         // chunk straddles f: scalar stores of the valid columns
-              __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy;
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.f) yr[c0 + j] = __float2bfloat16_rn(vl[j]);
+              for (int j = 0; j < 8; ++j) w8[j] = pack2(vl[2 * j], vl[2 * j + 1]);
+              st_row32(reinterpret_cast<__nv_bfloat16*>(p.y) + row * p.ldy + c0, w8);
             }
           } else {
-            if (c0 + 16 <= p.f) {
-              uint32_t wf[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) wf[j] = __float_as_uint(vl[j]);
-              store_rows64(stg, wf, reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(p.y) + row_w0 * p.ldy + c0),
-                           p.ldy * 4, rows_ok, lane);
-            } else if (row < p.n) {
-              float* yr = reinterpret_cast<float*>(p.y) + row * p.ldy;
+            for (int h8 = 0; h8 < 2; ++h8) {
+              if (c0 + h8 * 8 < p.f) {
+                uint32_t w8[8];
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.f) yr[c0 + j] = vl[j];
+                for (int j = 0; j < 8; ++j) w8[j] = __float_as_uint(vl[h8 * 8 + j]);
+                st_row32(reinterpret_cast<float*>(p.y) + row * p.ldy + c0 + h8 * 8, w8);
+              }
             }
           }
         }
-        if (p.y_bf16 && chunk_full)
-          store_rows64(stg, w16, reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(p.y) + row_w0 * p.ldy + c_lo + cc * 32),
-                       p.ldy * 2, rows_ok, lane);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -491,9 +463,10 @@ extern "C" int acm_fused_agg_fwd(const void* z, const void* d, const void* x, in
   ACM_CHECK_ARG(k >= 8 && k <= 256 && k % 8 == 0 && ldx >= k && ldw >= k, "fused_agg_fwd: need 8 <= k <= 256, k %% 8 == 0, ldx, ldw >= k");
   ACM_CHECK_ARG(f >= 1 && f <= fp, "fused_agg_fwd: need 1 <= f <= fp");
   ACM_CHECK_ARG(y_dtype == ACM_F32 || y_dtype == ACM_BF16, "fused_agg_fwd: bad y dtype %d", y_dtype);
-  ACM_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (ldy * (y_dtype == ACM_BF16 ? 2 : 4)) % 16 == 0,
-                "fused_agg_fwd: y must be 16-byte aligned with a 16-byte multiple row pitch");
-  ACM_CHECK_ARG(((reinterpret_cast<uintptr_t>(s_lh) | reinterpret_cast<uintptr_t>(h_i)) & 15) == 0, "fused_agg_fwd: s_lh / h_i must be 16-byte aligned");
+  ACM_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 31) == 0 && (ldy * (y_dtype == ACM_BF16 ? 2 : 4)) % 32 == 0 &&
+                    f % (y_dtype == ACM_BF16 ? 16 : 8) == 0,
+                "fused_agg_fwd: y must be 32-byte aligned with a 32-byte multiple row pitch and f a multiple of 16 (bf16) / 8 (fp32)");
+  ACM_CHECK_ARG(((reinterpret_cast<uintptr_t>(s_lh) | reinterpret_cast<uintptr_t>(h_i)) & 31) == 0, "fused_agg_fwd: s_lh / h_i must be 32-byte aligned");
   if (n_rows == 0) return 0;
   ACM_CHECK_ARG(n_rows < (1ll << 31) - BM, "fused_agg_fwd: more than 2^31 rows");
   Params p{};
@@ -508,7 +481,7 @@ extern "C" int acm_fused_agg_fwd(const void* z, const void* d, const void* x, in
   if ((rc = make_map(&md, d, (uint64_t)k, (uint64_t)n_rows, (uint64_t)ldx, BK, BM, "D"))) return rc;
   if ((rc = make_map(&mx, x, (uint64_t)k, (uint64_t)n_rows, (uint64_t)ldx, BK, BM, "X"))) return rc;
   if ((rc = make_map(&mw, wcat_t, (uint64_t)k, (uint64_t)(3 * FP), (uint64_t)ldw, BK, FP, "Wcat^T"))) return rc;
-  const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kStgBytes + 3 * FP * 4 + 64 + 2 * kParts * BM * 16 + 128 + 1024;
+  const size_t smem = (size_t)kStages * kStageBytes + 3 * FP * 4 + 64 + 2 * kParts * BM * 16 + 128 + 1024;
   cudaError_t e = cudaFuncSetAttribute(fused_agg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("fused_agg_fwd: smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e)); return (int)e; }
   int sms = 148, dev = 0;

@@ -151,7 +151,8 @@ def use_fused_forward(cfg: LayerConfig, impl: int, fp: int, f: int, k_channels: 
     only; y rows must be 16-byte aligned.  ``ACMB200_FUSED_FWD=off`` keeps the three GEMM launches plus the
     pre-aggregated epilogue launch."""
     return (impl == _lib.GEMM_TCGEN05 and cfg.dtype == "bf16" and fp == 256 and k_channels == 3 and not cfg.ln_live
-            and not cfg.variant and ldx % 8 == 0 and f % 8 == 0 and _knob("ACMB200_FUSED_FWD", FUSED_FWD_DEFAULT))
+            and not cfg.variant and ldx % 8 == 0 and f % (16 if cfg.out_dtype == "bf16" else 8) == 0
+            and _knob("ACMB200_FUSED_FWD", FUSED_FWD_DEFAULT))
 
 
 def use_local_table(cfg: LayerConfig, ldx: int, fp: int) -> bool:

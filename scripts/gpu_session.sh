@@ -54,9 +54,10 @@ for STEP in "$@"; do
       N=${REST%%:*}; A=""; [[ "$REST" == *:* ]] && A=${REST#*:}
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+i)) bench.py --gpus $N ${A//,/ } > ${O}_bench_g${N}_$i.log 2>&1
       echo "=== [$STEP] rc=$?"; grep -iE "error|Traceback" ${O}_bench_g${N}_$i.log | head -5; python -c "$SUM" < ${O}_bench_g${N}_$i.log ;;
-    dist)
-      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $REST --master-addr 127.0.0.1 --master-port $((29500+i)) scripts/dist_check.py > ${O}_dist_check_g${REST}.log 2>&1
-      echo "=== [$STEP] rc=$?"; grep -E "dist_check|DIST_CHECK|Error|FAIL" ${O}_dist_check_g${REST}.log | cut -c1-260 | tail -24 ;;
+    dist)     # dist:N[:VAR=VALUE]  (e.g. dist:4:ACMB200_PUSH=0 for the NCCL exchange path)
+      N=${REST%%:*}; E=""; [[ "$REST" == *:* ]] && E=${REST#*:}
+      env $E timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+i)) scripts/dist_check.py > ${O}_dist_check_g${N}_$i.log 2>&1
+      echo "=== [$STEP] rc=$?"; grep -E "DIST_CHECK|Error|FAIL" ${O}_dist_check_g${N}_$i.log | cut -c1-260 | tail -8; grep -c "> OK" ${O}_dist_check_g${N}_$i.log ;;
     nculist)
       timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${O}_launches_$i.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-stock-torch ${REST//,/ } > ${O}_nculist_$i.log 2>&1
       echo "=== [$STEP] rc=$?"; wc -l ${O}_launches_$i.csv ;;

@@ -469,7 +469,7 @@ def test_fused_tcgen05_forward_matches_unfused(n, fin, f, y_bf16, monkeypatch):
         finally:
             _lib.set_timer(None)
         names = set(k.split(":")[0] for k in timer.spans)
-        assert ("acm_fused_agg_fwd" in names) == (knob == "auto" and f % 8 == 0), names
+        assert ("acm_fused_agg_fwd" in names) == (knob == "auto" and f % (16 if y_bf16 else 8) == 0), names
         assert y.dtype == (torch.bfloat16 if y_bf16 else torch.float32)
         res[knob] = (y.detach().float().clone(), torch.cat([layer.att_low, layer.att_high, layer.att_mlp], 1).clone(),
                      {k: getattr(layer, k).grad.detach().clone() for k in ("weight_low", "weight_high", "weight_mlp", "att_vec_low", "att_vec")})
