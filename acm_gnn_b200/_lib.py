@@ -44,6 +44,7 @@ _PROTOS = {
     "acm_set_narrow_row_hint": [_i32],
     "acm_set_mix_bwd_occupancy": [_i32],
     "acm_set_mix_bwd_ring": [_i32],
+    "acm_set_gemm_direct_store": [_i32],
     "acm_gemm_ab": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "acm_gemm_atb": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp],
     "acm_spmm_agg_first": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
@@ -88,6 +89,9 @@ def load():
         r = os.environ.get("ACMB200_MIXBWD_RING")
         if r is not None:
             lib.acm_set_mix_bwd_ring(int(r))
+        ds = os.environ.get("ACMB200_GEMM_DIRECT")
+        if ds is not None:
+            lib.acm_set_gemm_direct_store(int(ds))
         o = os.environ.get("ACMB200_MIXBWD_OCC")
         if o is not None:
             lib.acm_set_mix_bwd_occupancy(int(o))

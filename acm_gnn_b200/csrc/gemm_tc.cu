@@ -86,6 +86,16 @@ __host__ __device__ __forceinline__ uint32_t make_idesc(int m, int n, int a_mn_m
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// 32 bytes of this thread's own output row in one 256-bit store (STG.E.256, sm_100): a whole sector per thread
+__device__ __forceinline__ void st_row32(void* dst, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 struct TnParams {
   int64_t m, n, k;       // problem
   int bn;                // UMMA_N / B box rows (multiple of 16, <= 256)
@@ -97,6 +107,9 @@ struct TnParams {
   int relu_cols;
   // MODE 1 (dX): fp32 output
   float* cf; int64_t ldcf; int vec_ok;
+  // every output row segment of 16 bf16 / 8 fp32 columns is 32-byte aligned: the epilogue writes it with ONE
+  // 256-bit store per thread straight from the TMEM registers (thread = row), no shared-memory transposition
+  int direct;
   // MODE 0: optional push of the c0 part ([HL|HH] rows) into every rank's table (peer memory)
   PeerTables peers;
 };
@@ -213,6 +226,36 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int c = half * 32; c < p.bn; c += 64) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.acc_cols + c), r);
+        if (p.direct) {
+          const int64_t row = m0 + q * 32 + lane;
+          if (row < p.m) {
+            if (MODE == 0) {
+#pragma unroll
+              for (int g2 = 0; g2 < 2; ++g2) {            // two groups of 16 columns
+                const int j = n0 + c + g2 * 16;
+                if (c + g2 * 16 >= p.bn || j >= p.n) continue;
+                uint32_t w[8];
+                const bool relu = j < p.relu_cols;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  float x0 = __uint_as_float(r[g2 * 16 + 2 * u]), x1 = __uint_as_float(r[g2 * 16 + 2 * u + 1]);
+                  if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+                  w[u] = pack2_bf16(x0, x1);
+                }
+                if (j < p.ncols0) st_row32(p.c0 + row * p.ldc0 + j, w);
+                else st_row32(p.c1 + row * p.ldc1 + (j - p.ncols0), w);
+              }
+            } else {
+#pragma unroll
+              for (int g4 = 0; g4 < 4; ++g4) {            // four groups of 8 fp32 columns
+                const int j = n0 + c + g4 * 8;
+                if (c + g4 * 8 >= p.bn || j >= p.n) continue;
+                st_row32(p.cf + row * p.ldcf + j, r + g4 * 8);
+              }
+            }
+          }
+          continue;
+        }
         // transpose through a per-warp staging tile (row stride 36 words: conflict-free v4
         // stores) so that global stores are row-contiguous full 32-byte sectors
 #pragma unroll
@@ -445,6 +488,8 @@ static int sm_count() {
   return sms;
 }
 
+int g_tn_direct = 1;   // acm_set_gemm_direct_store: 1 = 256-bit row stores when the output layout allows, 0 = staging tile
+
 template <int MODE>
 static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, TnParams p, cudaStream_t st) {
   if (p.m == 0) return 0;
@@ -466,6 +511,18 @@ static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, TnP
   if (rc) return rc;
   rc = make_map(&mb, b, (uint64_t)p.k, (uint64_t)p.n, (uint64_t)ldb, BK, (uint32_t)bn, "B operand");
   if (rc) return rc;
+  // Direct 256-bit row stores pay off when the epilogue's LATENCY is what limits the tile loop (K >= 128: forward
+  // X.Wcat 5.3 -> 4.7 ms at the headline size); a store-bound product with a short K loop (layer-1 dX: K = 48,
+  // 5 GB written) is faster through the transposition tile, whose store instructions cover 8 rows x 64 contiguous
+  // bytes instead of 32 rows x 32 bytes (measured 1.65 vs 2.2 ms) -> keep the tile there.
+  const bool k_long = p.k >= 128;
+  if (MODE == 0) {
+    const bool a0 = (reinterpret_cast<uintptr_t>(p.c0) & 31) == 0 && (p.ldc0 * 2) % 32 == 0 && p.ncols0 % 16 == 0;
+    const bool a1 = p.c1 == nullptr || ((reinterpret_cast<uintptr_t>(p.c1) & 31) == 0 && (p.ldc1 * 2) % 32 == 0);
+    p.direct = g_tn_direct && k_long && p.peers.n == 0 && a0 && a1 && p.n % 16 == 0 && p.relu_cols % 16 == 0;
+  } else {
+    p.direct = g_tn_direct && k_long && (reinterpret_cast<uintptr_t>(p.cf) & 31) == 0 && (p.ldcf * 4) % 32 == 0 && p.n % 8 == 0;
+  }
   const int64_t m_tiles = (p.m + BM - 1) / BM;
   ACM_CHECK_ARG(m_tiles * BM < (1ll << 31), "tcgen05 GEMM: more than 2^31 rows");
   p.total_tiles = m_tiles * p.n_tiles;
@@ -558,3 +615,8 @@ int tc_gemm_ab(const void* a, int64_t lda, const void* b_nk, int64_t ldb, void* 
 }
 
 }  // namespace acm
+
+extern "C" int acm_set_gemm_direct_store(int on) {
+  acm::tc::g_tn_direct = on ? 1 : 0;
+  return 0;
+}

@@ -11,6 +11,10 @@
  * Conventions
  *   - every pointer is a DEVICE pointer into memory owned by the caller (torch caching
  *     allocator); the library never allocates, frees or retains device memory;
+ *   - process-global state: a launch counter, a thread-local error string and the TUNING KNOBS set
+ *     through the acm_set_* entry points (gather mode, narrow-row hint, mix_bwd occupancy / ring,
+ *     GEMM store path).  The knobs select between implementations with identical results; they are
+ *     plain globals read at launch time -- set them once at start-up, not concurrently with launches;
  *   - `stream` is a cudaStream_t; every call is asynchronous on it, no internal
  *     device synchronisation;
  *   - return value 0 = success, otherwise a cudaError_t or ACM_ERR_* code and
@@ -204,6 +208,12 @@ int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
                      void* y, int y_dtype, int64_t ldy, void* o_save, float* att, float* sig,
                      const int32_t* long_rows, int n_long, const float* long_acc,
                      const int32_t* row_order, void* stream);
+
+/* Epilogue of the tcgen05 `tn` GEMMs (forward X.Wcat, dX, acm_gemm_ab): 1 (default) = every thread writes 32-byte
+ * pieces of its own output row with 256-bit stores straight from the TMEM registers whenever the output layout
+ * allows (32-byte aligned rows, column counts in multiples of 16 bf16 / 8 fp32); 0 = always go through the
+ * shared-memory transposition tile.  Bit-identical results. */
+int acm_set_gemm_direct_store(int on);
 
 /* Register/occupancy trade-off of mix_bwd_kernel (plain 3-channel mode): 2 (default) or 3 resident
  * CTAs per SM. */

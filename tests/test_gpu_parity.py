@@ -384,6 +384,39 @@ def test_input_backward_matches_oracle(fin, f, mode, monkeypatch):
             _close_grad(getattr(layer, k).grad, p[k].grad, mode, f"d{k} (BWD_INPUT={knob})")
 
 
+@pytest.mark.parametrize("variant", [False, True])
+@pytest.mark.parametrize("fin,f", [(128, 16), (136, 64), (256, 256), (200, 100), (128, 7), (48, 64)])
+def test_gemm_direct_store_is_bit_identical(fin, f, variant, monkeypatch):
+    """tcgen05 `tn` GEMM epilogue: 256-bit per-thread row stores (acm_set_gemm_direct_store(1), default) against the
+    shared-memory transposition tile (0) -- forward table, identity channel and dX must be bitwise equal; shapes whose
+    layout does not allow the direct path (f = 7: 24 output columns) silently take the tile in both settings."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    monkeypatch.setenv("ACMB200_REORDER", "off")
+    monkeypatch.setenv("ACMB200_BWD_INPUT", "off")
+    os.environ["ACMB200_DTYPE"] = "bf16"
+    torch.manual_seed(fin + f)
+    n = 1531
+    row, col = O.synthetic_edges(n, 20000, seed=1)
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    layer = A.GraphConvolution(fin, f, n, "acmgcn", variant=variant).cuda()
+    x = torch.randn(n, fin, device="cuda")
+    w = torch.randn(n, f, device="cuda")
+    res = []
+    try:
+        for knob in (1, 0):
+            _lib.call("acm_set_gemm_direct_store", knob)
+            xc = x.clone().requires_grad_(True)
+            y = layer(xc, op, None, None)
+            (y * w).sum().backward()
+            torch.cuda.synchronize()
+            res.append((y.detach().clone(), xc.grad.clone()))
+    finally:
+        _lib.call("acm_set_gemm_direct_store", 1)
+    assert torch.isfinite(res[0][0]).all() and torch.isfinite(res[0][1]).all()
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("f", [64, 100, 256])
 def test_rank1_backward_table_matches_oracle(f, mode, monkeypatch):
