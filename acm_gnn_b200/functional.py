@@ -530,7 +530,10 @@ class AcmLayerFunction(torch.autograd.Function):
 
         dh_all = torch.empty(n, 3 * fp, dtype=tdt, device=dev)
         dos_pre = torch.empty(n, fp, dtype=tdt, device=dev) if K == 4 else None
-        dpack = torch.zeros(12 * fp + 16, dtype=torch.float32, device=dev)
+        # parameter-gradient accumulators of this layer in ONE buffer: [dwcat (fin x 3fp) | dpack]  -> one memset and,
+        # under a row partition, one all-reduce instead of two
+        gbuf = torch.zeros(fin * 3 * fp + 12 * fp + 16, dtype=torch.float32, device=dev)
+        dpack = gbuf[fin * 3 * fp:]
         needs_t = not (ctx.agg_first or ctx.bwd_input)      # a transposed aggregation follows
         rank1 = needs_t and use_rank1_table(cfg, op, fp)
         tw = (fp + (8 if cfg.dtype == "bf16" else 4)) if rank1 else 2 * fp     # table bytes per row / element size
@@ -552,7 +555,7 @@ class AcmLayerFunction(torch.autograd.Function):
                       float(cfg.out_scale), t_lh.data_ptr(), int(rank1), n, dh_all.data_ptr(), _lib.ptr(dos_pre), dpack.data_ptr(),
                       0, 0, 0, 0, st, tag=fp)
 
-        dwcat = torch.zeros(fin, 3 * fp, dtype=torch.float32, device=dev)
+        dwcat = gbuf[:fin * 3 * fp].view(fin, 3 * fp)
         dx = None
         if ctx.bwd_input:
             # transform-first forward, input without gradient: aggregate the input rows here instead of
@@ -627,8 +630,7 @@ class AcmLayerFunction(torch.autograd.Function):
                 del dos_all, d_loc
 
         if cfg.dist is not None:
-            cfg.dist.all_reduce_(dwcat)
-            cfg.dist.all_reduce_(dpack)
+            cfg.dist.all_reduce_(gbuf)
 
         # one launch splits dwcat / dpack into the reference's parameter shapes
         dw = [torch.empty(fin, f, dtype=torch.float32, device=dev) for _ in range(3)]

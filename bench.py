@@ -790,6 +790,15 @@ def run_ours(args):
 
     if north is not None and roof is not None:
         roof["north_star"] = north["roofline"]     # both kernels inside the contract's roofline object
+    kfu = f"acm_fused_agg_fwd:{fp0}"
+    if roof is not None and kfu in summ:
+        # fused tcgen05 forward of layer 0 (three GEMMs + attention/mix epilogue, accumulators in TMEM): streams Z, D, X
+        # once and writes [S_L|S_H], HI, Y, att, sig once
+        cnt, ms = summ[kfu]
+        fb = n_loc * (3 * fpx * s_el + 2 * fp0 * s_el + fp0 * s_el + hid * y_el + 24)
+        roof["fused_forward"] = {"kernel": "fused_agg_fwd_kernel (tcgen05 GEMMs + attention/mix epilogue, layer 0)", "bound": "hbm",
+                                 "achieved": fb / (ms / cnt * 1e-3) / 1e9, "frac": fb / (ms / cnt * 1e-3) / 1e9 / roof["peak"], "unit": "GB/s",
+                                 "algorithmic_bytes_per_launch": fb, "avg_launch_ms": ms / cnt, "launches_timed": cnt}
 
     # ---- A/B of the narrow-row gather hint (layer 1: 64-byte table rows) in the same process ----
     hint_ab = None

@@ -63,7 +63,7 @@ for STEP in "$@"; do
       echo "=== [$STEP] rc=$?"; wc -l ${O}_launches_$i.csv ;;
     ncufull)
       RX=${REST%%:*}; A=""; [[ "$REST" == *:* ]] && A=${REST#*:}
-      timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"$RX" -c 8 -o /tmp/prof_${TAG}_$i python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-stock-torch ${A//,/ } > ${O}_ncufull_$i.log 2>&1
+      timeout 1200 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"$RX" -c 20 -o /tmp/prof_${TAG}_$i python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-stock-torch ${A//,/ } > ${O}_ncufull_$i.log 2>&1
       echo "=== [$STEP] rc=$?"
       ncu -i /tmp/prof_${TAG}_$i.ncu-rep --page raw --csv > ${O}_ncu_raw_$i.csv 2>/dev/null
       ncu -i /tmp/prof_${TAG}_$i.ncu-rep --page details > ${O}_ncu_details_$i.txt 2>/dev/null
