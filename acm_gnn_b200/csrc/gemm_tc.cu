@@ -115,8 +115,9 @@ struct TnParams {
 };
 
 constexpr int kStgLd = 36;                           // staging row stride in words (32 + 4 pad)
-constexpr int kTnEpiWarps = 8;                       // two warps per 32-lane TMEM quadrant
-constexpr int kTnThreads = 64 + 32 * kTnEpiWarps;    // + producer warp + MMA warp
+// EPI = epilogue warps: 8 (two per 32-lane TMEM quadrant) or, for store-bound products with a short K loop where
+// the epilogue is the critical path of the tile loop, 16 (four per quadrant)
+template <int EPI> struct TnCfg { static constexpr int kThreads = 64 + 32 * EPI; };   // + producer warp + MMA warp
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -125,9 +126,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Persistent kernel: one CTA per SM walks tiles (n fastest, so neighbouring CTAs share the A
 // tile in L2); the TMA/MMA ring runs continuously across tiles and the accumulator is double
 // buffered in TMEM, so the epilogue of tile t overlaps the main loop of tile t+1.
-template <int MODE>
-__global__ void __launch_bounds__(kTnThreads, 1)
+template <int MODE, int EPI>
+__global__ void __launch_bounds__(TnCfg<EPI>::kThreads, 1)
 tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TnParams p) {
+  constexpr int kTnEpiWarps = EPI;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = BM * BK * 2;
@@ -214,7 +216,7 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32); the two warps of a
     // quadrant take alternating 32-column chunks
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int part = (warp - 2) >> 2;
     float* stg = reinterpret_cast<float*>(smem_raw + (tmem_slot + 16 - smem_u32(smem_raw))) + (warp - 2) * (32 * kStgLd);
     int t = 0;
     for (int64_t tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
@@ -223,7 +225,7 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int64_t m0 = (tile / p.n_tiles) * BM;
       mbar_wait(tfull + 8 * a, (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c = half * 32; c < p.bn; c += 64) {
+      for (int c = part * 32; c < p.bn; c += 32 * (EPI / 4)) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.acc_cols + c), r);
         if (p.direct) {
@@ -490,8 +492,10 @@ static int sm_count() {
 
 int g_tn_direct = 1;   // acm_set_gemm_direct_store: 1 = 256-bit row stores when the output layout allows, 0 = staging tile
 
-template <int MODE>
-static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, TnParams p, cudaStream_t st) {
+template <int MODE, int EPI>
+static int launch_tn_epi(const void* a, int64_t lda, const void* b, int64_t ldb, TnParams p, cudaStream_t st) {
+  constexpr int kTnEpiWarps = EPI;
+  constexpr int kTnThreads = TnCfg<EPI>::kThreads;
   if (p.m == 0) return 0;
   int bn = (int)((p.n < 256 ? p.n : 256));
   bn = (bn + 15) / 16 * 16;
@@ -527,11 +531,21 @@ static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, TnP
   ACM_CHECK_ARG(m_tiles * BM < (1ll << 31), "tcgen05 GEMM: more than 2^31 rows");
   p.total_tiles = m_tiles * p.n_tiles;
   const int64_t grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-  cudaError_t e = cudaFuncSetAttribute(tn_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(tn_kernel<MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("tcgen05 GEMM: smem attribute: %s", cudaGetErrorString(e)); return (int)e; }
-  tn_kernel<MODE><<<(unsigned)grid, kTnThreads, smem, st>>>(ma, mb, p);
+  tn_kernel<MODE, EPI><<<(unsigned)grid, kTnThreads, smem, st>>>(ma, mb, p);
   ACM_LAUNCH_CHECK("tcgen05 gemm_tn");
   return 0;
+}
+
+int g_tn_epi16 = 1;   // store-bound short-K products: 16 epilogue warps (acm_set_gemm_direct_store bit 1 clears it)
+
+template <int MODE>
+static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, const TnParams& p, cudaStream_t st) {
+  // a short K loop (layer-1 dX: K = 48) makes the tile loop epilogue-bound: measured 1.65 ms = 3.7 TB/s for 6 GB with
+  // 8 epilogue warps -> four warps per TMEM quadrant there
+  if (g_tn_epi16 && p.k < 128 && p.n >= 128 && p.peers.n == 0) return launch_tn_epi<MODE, 16>(a, lda, b, ldb, p, st);
+  return launch_tn_epi<MODE, 8>(a, lda, b, ldb, p, st);
 }
 
 }  // namespace tc
@@ -617,6 +631,7 @@ int tc_gemm_ab(const void* a, int64_t lda, const void* b_nk, int64_t ldb, void* 
 }  // namespace acm
 
 extern "C" int acm_set_gemm_direct_store(int on) {
-  acm::tc::g_tn_direct = on ? 1 : 0;
+  acm::tc::g_tn_direct = (on & 1) ? 1 : 0;
+  acm::tc::g_tn_epi16 = (on & 2) ? 0 : 1;     // bit 1 set: keep 8 epilogue warps for short-K products too (A/B switch)
   return 0;
 }

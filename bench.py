@@ -454,6 +454,14 @@ def stock_torch_gpu(args, dev):
         return {"error": repr(e)[:300]}
 
 
+def _traffic(key):
+    """ncu-measured DRAM bytes per launch (profiles/traffic.json), or None when this shape was not captured."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key)
+    except Exception:
+        return None
+
+
 def bind_to_gpu_numa_node(local_rank):
     """Pin this rank's host threads to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host
     buffer is allocated (first-touch places the pages on that node).  Round 1's e2e numbers were flat from 2 to
@@ -798,7 +806,8 @@ def run_ours(args):
         fb = n_loc * (3 * fpx * s_el + 2 * fp0 * s_el + fp0 * s_el + hid * y_el + 24)
         roof["fused_forward"] = {"kernel": "fused_agg_fwd_kernel (tcgen05 GEMMs + attention/mix epilogue, layer 0)", "bound": "hbm",
                                  "achieved": fb / (ms / cnt * 1e-3) / 1e9, "frac": fb / (ms / cnt * 1e-3) / 1e9 / roof["peak"], "unit": "GB/s",
-                                 "algorithmic_bytes_per_launch": fb, "avg_launch_ms": ms / cnt, "launches_timed": cnt}
+                                 "algorithmic_bytes_per_launch": fb, "avg_launch_ms": ms / cnt, "launches_timed": cnt,
+                                 "traffic": _traffic(f"{kfu}:N{args.nodes}:E{args.edges}:{args.dtype}:w{world}")}
 
     # ---- A/B of the narrow-row gather hint (layer 1: 64-byte table rows) in the same process ----
     hint_ab = None
