@@ -144,6 +144,48 @@ template <typename T> __device__ __forceinline__ void cp_async_slice(uint32_t ds
   if (sizeof(T) == 4) cp_async16(dst + 16, reinterpret_cast<const char*>(src) + 16);
 }
 
+// ---- packed fp32 arithmetic (sm_100: FFMA2 / FMUL2, two IEEE fp32 results per issue slot) ----------------------
+// The row kernels are ISSUE bound (mix_bwd: 72 % of the issue slots for 88 % of the HBM peak); their inner loops are
+// per-feature FMAs over 8-feature slices, i.e. natural pairs.  Each lane of a pair is a plain fma.rn.f32: bit-identical
+// to the scalar form.
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+// acc[0..8) += w * f[0..8)   (four FFMA2)
+__device__ __forceinline__ void axpy8(float (&acc)[8], const float w, const float (&f)[8]) {
+  const float2 w2 = make_float2(w, w);
+#pragma unroll
+  for (int t = 0; t < 8; t += 2) {
+    const float2 r = ffma2(w2, make_float2(f[t], f[t + 1]), make_float2(acc[t], acc[t + 1]));
+    acc[t] = r.x;
+    acc[t + 1] = r.y;
+  }
+}
+// sum_t a[t] * b[t] over 8 features: two-lane partial sums (four FFMA2) + one add.  NOTE: a different summation
+// order than the 8-long scalar FMA chain -- used where the value feeds a reduction anyway.
+__device__ __forceinline__ float dot8(const float (&a)[8], const float (&b)[8]) {
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int t = 0; t < 8; t += 2) s = ffma2(make_float2(a[t], a[t + 1]), make_float2(b[t], b[t + 1]), s);
+  return s.x + s.y;
+}
+
 extern int g_gather_mode;       // spmm_fwd.cu; set by acm_set_gather_mode
 
 // reduce over the LANES lanes of one row group (LANES is a power of two <= 32; groups are

@@ -287,10 +287,7 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
     float adot = 0.f;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
-      float d = 0.f;
-#pragma unroll
-      for (int t = 0; t < 8; ++t) d = fmaf(G[t], o[k][t], d);
-      dal[k] = c * group_sum<LANES>(d);
+      dal[k] = c * group_sum<LANES>(dot8(G, o[k]));
       adot = fmaf(al[k], dal[k], adot);
     }
 #pragma unroll
@@ -314,10 +311,13 @@ __global__ void __launch_bounds__(kBwdWarps * 32, MINB) mix_bwd_kernel(const Bwd
       if (!LN) {
         float ak[8];
         load_smem8(s_a + k * FP + f0, ak);
+        axpy8(da[k], dz[k], o[k]);
+        const float2 ca2 = make_float2(c * al[k], c * al[k]), dz2 = make_float2(dz[k], dz[k]);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          da[k][t] = fmaf(dz[k], o[k][t], da[k][t]);
-          dO[k][t] = fmaf(c * al[k], G[t], dz[k] * ak[t]);
+        for (int t = 0; t < 8; t += 2) {
+          const float2 r = ffma2(ca2, make_float2(G[t], G[t + 1]), fmul2(dz2, make_float2(ak[t], ak[t + 1])));
+          dO[k][t] = r.x;
+          dO[k][t + 1] = r.y;
         }
       } else {
         float s1 = 0.f;

@@ -178,14 +178,10 @@ spmm_t_rank1_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ ro
     sc.w = __shfl_sync(gmask, sc.w, sub * LANES);
     float f[8];
     v.to_float(f);
-    const float wl = w * sc.x, wh = w * sc.y;
     sL = fmaf(w, sc.z, sL);
     sH = fmaf(w, sc.w, sH);
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      accL[t] = fmaf(wl, f[t], accL[t]);
-      accH[t] = fmaf(wh, f[t], accH[t]);
-    }
+    axpy8(accL, w * sc.x, f);
+    axpy8(accH, w * sc.y, f);
     if (i + ST < n_e) {
       const int64_t c = __ldg(col + e + i + ST);
       cp_async_slice<T>(ring_u32 + slot * STAGE, table + c * FP + gl * 8);
