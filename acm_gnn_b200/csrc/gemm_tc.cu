@@ -550,6 +550,26 @@ static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, con
 
 }  // namespace tc
 
+// uint32 2-D tensor map without swizzle (the TMA row gather of spmm_fwd.cu: box {box_inner x box_outer})
+int tma_encode_2d_u32(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                      uint32_t box_inner, uint32_t box_outer, const char* what) {
+  tc::EncodeTiledFn enc = tc::get_encode();
+  if (!enc) { set_error("TMA: cuTensorMapEncodeTiled entry point unavailable"); return ACM_ERR_UNSUPPORTED; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || pitch_bytes % 16) {
+    set_error("TMA: %s must be 16-byte aligned with a row pitch that is a multiple of 16 bytes", what);
+    return ACM_ERR_BAD_ARG;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("TMA: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return ACM_ERR_BAD_ARG; }
+  return 0;
+}
+
 int tc_gemm_fwd(const void* x, int64_t ldx, const void* wcat_t, void* h_lh, void* h_i, int64_t n, int64_t fin,
                 int64_t fp, int relu_lh, const PeerTables* peers, cudaStream_t st) {
   tc::TnParams p{};

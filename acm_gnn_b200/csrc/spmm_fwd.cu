@@ -10,6 +10,8 @@
 // features of every channel, so the whole epilogue is lane-local except K (or 3K with
 // LayerNorm) group reductions.  Per edge a lane issues two 16-byte loads (bf16) from the
 // neighbour's table row: features [8g,8g+8) of HL and of HH.  Accumulation is fp32.
+#include <cuda.h>
+
 #include "acm_common.cuh"
 
 namespace acm {
@@ -70,6 +72,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// ---- TMA row gather (gather mode 3, FP = 256 in bf16: one row per warp) --------------------------------------
+// sm_100's cp.async.bulk.tensor ... tile::gather4 fetches FOUR rows of a 2-D tensor, given by four row indices, with one
+// instruction of the TMA engine: the "TMA-staged feature tiles" of the north star.  The [N, 2*FP] bf16 table is
+// described to the engine as a uint32 [N, 256] tensor with a {256 x 1} box (established with scripts/gather4_probe.cu:
+// a box of 4 rows is an illegal instruction, the four rows land back to back in shared memory, 4 KB per request).
+// One elected lane issues a request per group of four edges into a kTmaStages-deep ring of 4-KB stages, completion
+// by one mbarrier per stage; every lane then reads its own two 16-byte slices of each of the four rows.
+constexpr int kTmaStages = 3;
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int r0, int r1, int r2, int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
 }
 
 // ---- epilogue: attention (optional LayerNorm, sigmoid, KxK mix, softmax), weighted sum, stores ----
@@ -196,7 +212,7 @@ __device__ __forceinline__ void fwd_epilogue(const FwdParams& p, const int64_t r
 template <typename T, int FP, int MODE, int GM>
 __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t rb, const float* s_a,
                                               const float* s_avec, const float* s_ga, const float* s_sc,
-                                              uint8_t* s_ring) {
+                                              uint8_t* s_ring, const CUtensorMap* tmap = nullptr) {
   constexpr int LANES = FP / 8;
   constexpr int RPW = 32 / LANES;
   constexpr bool LN = (MODE & 1) != 0;   // LayerNorm of the attention logits live (ACM-Geometric flavour)
@@ -282,6 +298,63 @@ __device__ __forceinline__ void fwd_row_block(const FwdParams& p, const int64_t 
       if (lane == 0 && j < n_e) {
         mbar_expect_tx(bar_u32 + slot * 8, ROWB);
         bulk_copy_g2s(ring_u32 + slot * ROWB, tab0 + (int64_t)cn * TW, ROWB, bar_u32 + slot * 8);
+      }
+    }
+    e = e1;
+  }
+
+  if (GM == 5 && LANES == 32 && sizeof(T) == 2 && e < e1) {
+    constexpr int ST = kTmaStages;
+    constexpr uint32_t STAGE = 4 * TW * (uint32_t)sizeof(T);      // four table rows = 4 KB
+    uint8_t* ring = s_ring + warp * (ST * STAGE);
+    const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+    const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(s_ring + kFwdWarps * (ST * STAGE)) + warp * (ST * 8);
+    const int n_e = (int)(e1 - e);
+    const int n_grp = (n_e + 3) >> 2;
+    // column indices / weights travel in registers, 32 edges (8 groups) per coalesced load, broadcast by shuffle;
+    // edges past the end of the row gather row 0 with weight 0
+    int32_t ccur = (lane < n_e) ? __ldg(col + e + lane) : 0;
+    float wcur = (lane < n_e) ? (val ? __ldg(val + e + lane) : 1.f) : 0.f;
+    int32_t cnext = ccur;                                          // indices of the 32 edges the issue side is in
+    auto issue = [&](int grp, int stage) {                         // all lanes call it (shuffles), lane 0 issues
+      const int b = (grp * 4) & 31;
+      const int r0 = __shfl_sync(0xffffffffu, cnext, b), r1 = __shfl_sync(0xffffffffu, cnext, b + 1);
+      const int r2 = __shfl_sync(0xffffffffu, cnext, b + 2), r3 = __shfl_sync(0xffffffffu, cnext, b + 3);
+      if (lane == 0) {
+        mbar_expect_tx(bar_u32 + stage * 8, STAGE);
+        tma_gather4(ring_u32 + stage * STAGE, tmap, r0, r1, r2, r3, bar_u32 + stage * 8);
+      }
+    };
+#pragma unroll
+    for (int st = 0; st < ST; ++st)
+      if (st < n_grp) issue(st, st);                               // ST * 4 <= 32: all inside the first index chunk
+    for (int g = 0; g < n_grp; ++g) {
+      const int stage = g % ST;
+      if (((g * 4) & 31) == 0 && g) {
+        const int i0 = g * 4;
+        wcur = (i0 + lane < n_e) ? (val ? __ldg(val + e + i0 + lane) : 1.f) : 0.f;
+      }
+      mbar_wait(bar_u32 + stage * 8, (g / ST) & 1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float w = __shfl_sync(0xffffffffu, wcur, (g * 4 + u) & 31);
+        Slice8<T> vl, vh;
+        vl.load_plain(reinterpret_cast<const T*>(ring + stage * STAGE + u * (TW * sizeof(T)) + lane * 16));
+        vh.load_plain(reinterpret_cast<const T*>(ring + stage * STAGE + u * (TW * sizeof(T)) + FP * sizeof(T) + lane * 16));
+        float fl[8], fh[8];
+        vl.to_float(fl);
+        vh.to_float(fh);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          accL[t] = fmaf(w, fl[t], accL[t]);
+          accH[t] = fmaf(w, fh[t], accH[t]);
+        }
+      }
+      __syncwarp();                                                // every lane has read the stage
+      const int j = g + ST;                                        // group whose rows re-fill this stage
+      if (j < n_grp) {
+        if (((j * 4) & 31) == 0) cnext = ((j * 4) + lane < n_e) ? __ldg(col + e + j * 4 + lane) : 0;
+        issue(j, stage);
       }
     }
     e = e1;
@@ -510,7 +583,40 @@ __global__ void __launch_bounds__(kFwdWarps * 32, GM == 4 ? 3 : 1) spmm_mix_fwd_
   }
 }
 
-int g_gather_mode = 1;  // 0: LDG register staging, 1: cp.async ring, 2: cp.async.bulk ring (FP = 256)
+// gather mode 3: same row block, neighbour rows staged by the TMA engine (tile::gather4); FP = 256, bf16 tables
+template <typename T, int FP, int MODE>
+__global__ void __launch_bounds__(kFwdWarps * 32, 1)
+spmm_mix_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParams p) {
+  constexpr bool LN = (MODE & 1) != 0;
+  constexpr int KMAX = (MODE & 2) ? 4 : 3;
+  extern __shared__ __align__(128) uint8_t smem_tma[];
+  // the dynamic shared window is only guaranteed 16-byte aligned: round up to the 128 bytes a TMA destination needs
+  float* smem = reinterpret_cast<float*>(smem_tma + ((128u - ((uint32_t)__cvta_generic_to_shared(smem_tma) & 127u)) & 127u));
+  float* s_a = smem;
+  float* s_avec = s_a + KMAX * FP;
+  float* s_ga = s_avec + 16;
+  float* s_sc = s_ga + (LN ? KMAX * FP : 0);
+  for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) s_a[i] = p.pack[i];
+  if (threadIdx.x < 16) s_avec[threadIdx.x] = p.pack[pack_off_avec(FP) + threadIdx.x];
+  if (LN) {
+    for (int i = threadIdx.x; i < KMAX * FP; i += blockDim.x) s_ga[i] = p.pack[pack_off_ga(FP, 0) + i];
+    if (threadIdx.x < 4) s_sc[threadIdx.x] = p.pack[pack_off_sum_ba(FP) + threadIdx.x];
+  }
+  constexpr int kPackFloats = KMAX * FP + 16 + (LN ? KMAX * FP + 8 : 0);
+  uint8_t* s_ring = reinterpret_cast<uint8_t*>(smem + ((kPackFloats + 31) & ~31));     // 128-byte aligned stages
+  constexpr uint32_t STAGE = 4 * 2 * FP * (uint32_t)sizeof(T);
+  if (threadIdx.x < kFwdWarps * kTmaStages)
+    mbar_init((uint32_t)__cvta_generic_to_shared(s_ring + kFwdWarps * kTmaStages * STAGE) + threadIdx.x * 8, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  fwd_row_block<T, FP, MODE, 5>(p, blockIdx.x, s_a, s_avec, s_ga, s_sc, s_ring, &tmap);
+}
+
+int tma_encode_2d_u32(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                      uint32_t box_inner, uint32_t box_outer, const char* what);   // gemm_tc.cu
+
+int g_gather_mode = 1;  // 0: LDG register staging, 1: cp.async ring, 2: cp.async.bulk ring, 3: TMA tile::gather4 (FP = 256, bf16)
 
 template <typename K>
 static int raise_smem(K kernel, size_t smem) {
@@ -535,6 +641,20 @@ static int launch_fwd(const FwdParams& p, cudaStream_t st) {
   // the ring pays off for wide rows (FP = 256: 97 % vs 91 % of HBM peak); for narrow rows (FP = 16,
   // two lanes per row) the per-edge commit/wait overhead costs more than it hides (measured 5.4 vs
   // 4.8 ms), so they keep the register-staged LDG loop
+  if constexpr (FP == 256 && sizeof(T) == 2) {
+    if (!p.pre_agg && g_gather_mode == 3) {
+      // north-star wording: neighbour rows staged in shared memory by the TMA engine (4 rows per request)
+      CUtensorMap tm;
+      // the row extent only bounds the coordinates the engine accepts: column ids are < the number of table rows by
+      // construction of the CSR, so the largest extent the descriptor can hold is as good as the true one
+      if (int rc = tma_encode_2d_u32(&tm, p.table, 256, 0x7fffffffull, 1024, 256, 1, "gather table")) return rc;
+      size_t smem_t = sizeof(float) * ((kPackFloats + 31) & ~31) + (size_t)kFwdWarps * kTmaStages * (4 * 2 * FP * sizeof(T) + 8) + 128;
+      if (int rc = raise_smem(spmm_mix_fwd_tma_kernel<T, FP, MODE>, smem_t)) return rc;
+      spmm_mix_fwd_tma_kernel<T, FP, MODE><<<(unsigned)blocks, kFwdWarps * 32, smem_t, st>>>(tm, p);
+      ACM_LAUNCH_CHECK("spmm_mix_fwd (TMA gather)");
+      return 0;
+    }
+  }
   const int gm = p.pre_agg ? 4
                  : (g_gather_mode == 2 && FP == 256) ? 2
                  : (g_gather_mode >= 1 && FP >= 64) ? 1 : 0;
@@ -611,8 +731,8 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
 }
 
 extern "C" int acm_set_gather_mode(int mode) {
-  if (mode < 0 || mode > 2) {
-    acm::set_error("gather mode must be 0 (LDG), 1 (cp.async ring) or 2 (cp.async.bulk ring)");
+  if (mode < 0 || mode > 3) {
+    acm::set_error("gather mode must be 0 (LDG), 1 (cp.async ring), 2 (cp.async.bulk ring) or 3 (TMA tile::gather4)");
     return ACM_ERR_BAD_ARG;
   }
   acm::g_gather_mode = mode;

@@ -48,6 +48,9 @@ for STEP in "$@"; do
       timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > ${O}_smoke.log 2>&1; echo "=== [smoke] rc=$?"; tail -3 ${O}_smoke.log ;;
     ref)
       timeout 900 python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 ${REST//,/ } > ${O}_bench_reference_$i.log 2>&1; echo "=== [$STEP] rc=$?"; tail -1 ${O}_bench_reference_$i.log | cut -c1-500 ;;
+    ebench)   # ebench:VAR=VALUE[:args]  -- bench.py with one environment variable set (A/B of a knob on the same box)
+      E=${REST%%:*}; A=""; [[ "$REST" == *:* ]] && A=${REST#*:}
+      env $E timeout 1200 python bench.py ${A//,/ } > ${O}_bench_$i.log 2>&1; echo "=== [$STEP] rc=$?"; python -c "$SUM" < ${O}_bench_$i.log ;;
     bench)
       timeout 1200 python bench.py ${REST//,/ } > ${O}_bench_$i.log 2>&1; echo "=== [$STEP] rc=$?"; tail -3 ${O}_bench_$i.log | cut -c1-300 | grep -v '^{' ; python -c "$SUM" < ${O}_bench_$i.log ;;
     mbench)

@@ -634,10 +634,11 @@ def test_degree_skew_long_rows_squirrel(order, mode, monkeypatch):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-@pytest.mark.parametrize("gather", [1, 2])
+@pytest.mark.parametrize("gather", [1, 2, 3])
 def test_gather_modes_agree_wide_rows(gather, mode):
     """Width 256 (one row per warp) is where gather mode 2 (cp.async.bulk ring, one 1-KB copy per
-    neighbour row) applies.  Degrees from 1 to > 100 exercise the ring wrap-around (8 / 4 slots)
+    neighbour row) and mode 3 (TMA tile::gather4: four neighbour rows per request of the TMA engine, bf16 tables;
+    fp32 tables fall back to the cp.async ring) apply.  Degrees from 1 to > 100 exercise the ring wrap-around (8 / 4 slots)
     and the 32-edge register chunks of column indices and weights.  Same accumulation order in
     every mode -> bitwise equal outputs."""
     import acm_gnn_b200 as A
@@ -665,7 +666,7 @@ def test_gather_modes_agree_wide_rows(gather, mode):
         os.environ.pop("ACMB200_REORDER", None)
 
 
-@pytest.mark.parametrize("gather", ["0", "1", "2"])
+@pytest.mark.parametrize("gather", ["0", "1", "2", "3"])
 def test_gather_modes_agree(gather):
     """acm_set_gather_mode: the cp.async shared-memory ring and the LDG register-staged gather
     produce the same sums (fp32 storage: identical accumulation order -> bitwise equal)."""
