@@ -1,5 +1,6 @@
 // Shared device/host helpers for libacm_b200 (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -143,6 +144,35 @@ template <typename T> __device__ __forceinline__ void cp_async_slice(uint32_t ds
   cp_async16(dst, src);
   if (sizeof(T) == 4) cp_async16(dst + 16, reinterpret_cast<const char*>(src) + 16);
 }
+
+// ---- mbarrier + TMA row gather (sm_100) -------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+// cp.async.bulk.tensor ... tile::gather4: FOUR rows of a 2-D tensor, given by four row indices, in one request of the
+// TMA engine; they land back to back at `dst` (4 x box bytes) and complete `bar`.  Tensor map: box {row_words x 1}
+// (scripts/gather4_probe.cu: a 4-row box is an illegal instruction), no swizzle.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int r0, int r1, int r2, int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst), "l"(map), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
+// host: uint32 2-D tensor map without swizzle (gemm_tc.cu)
+int tma_encode_2d_u32(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                      uint32_t box_inner, uint32_t box_outer, const char* what);
 
 // ---- packed fp32 arithmetic (sm_100: FFMA2 / FMUL2, two IEEE fp32 results per issue slot) ----------------------
 // The row kernels are ISSUE bound (mix_bwd: 72 % of the issue slots for 88 % of the HBM peak); their inner loops are

@@ -53,22 +53,6 @@ template <typename T> struct AsyncCfg { static constexpr int kStages = sizeof(T)
 // cp.async.bulk (the TMA engine's linear-copy form, SASS UBLKCP) issued by lane 0 replaces the
 // 64 per-lane LDGSTS of mode 1; completion is tracked per ring slot by an mbarrier
 // (arrive.expect_tx by the issuing lane, complete_tx by the copy engine).
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  } while (!ok);
-}
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -81,12 +65,7 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
 // a box of 4 rows is an illegal instruction, the four rows land back to back in shared memory, 4 KB per request).
 // One elected lane issues a request per group of four edges into a kTmaStages-deep ring of 4-KB stages, completion
 // by one mbarrier per stage; every lane then reads its own two 16-byte slices of each of the four rows.
-constexpr int kTmaStages = 3;
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int r0, int r1, int r2, int r3, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-      ::"r"(dst), "l"(map), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
-}
+constexpr int kTmaStages = 2;   // x 4 rows x 1 KB per warp: 64 KB per CTA -> 3 CTAs per SM (3 stages / 2 CTAs per SM measured 39.0 vs 34.6 ms)
 
 // ---- epilogue: attention (optional LayerNorm, sigmoid, KxK mix, softmax), weighted sum, stores ----
 // o[k][t]: the channel outputs O_k of this lane's 8 features (already relu'd as the variant asks;
@@ -613,10 +592,7 @@ spmm_mix_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const FwdParam
   fwd_row_block<T, FP, MODE, 5>(p, blockIdx.x, s_a, s_avec, s_ga, s_sc, s_ring, &tmap);
 }
 
-int tma_encode_2d_u32(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                      uint32_t box_inner, uint32_t box_outer, const char* what);   // gemm_tc.cu
-
-int g_gather_mode = 1;  // 0: LDG register staging, 1: cp.async ring, 2: cp.async.bulk ring, 3: TMA tile::gather4 (FP = 256, bf16)
+int g_gather_mode = 3;  // 0: LDG register staging, 1: cp.async ring, 2: cp.async.bulk ring, 3 (default): TMA tile::gather4 where it applies (width 256, bf16), else 1
 
 template <typename K>
 static int raise_smem(K kernel, size_t smem) {

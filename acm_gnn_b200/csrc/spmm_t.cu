@@ -350,6 +350,95 @@ spmm_agg_first_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ 
   Slice8<T>::store(d_out + row * FP + gl * 8, d);
 }
 
+// The same aggregation with the neighbour rows staged by the TMA engine (tile::gather4, four 512-byte rows per request
+// into a 4-stage ring of 2-KB stages per warp; see spmm_fwd.cu gather mode 3, where the technique beat the cp.async ring
+// 34.6 vs 37.4 ms).  Input width 256 in bf16: one row per warp, a lane owns 16 bytes of every row.
+constexpr int kAggTmaStages = 4;
+__global__ void __launch_bounds__(kTWarps * 32)
+spmm_agg_first_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_rows, int64_t row0,
+                          const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                          const __nv_bfloat16* __restrict__ table, __nv_bfloat16* __restrict__ z_out,
+                          __nv_bfloat16* __restrict__ d_out, const LongRows lr) {
+  using T = __nv_bfloat16;
+  constexpr int FP = 256;
+  constexpr int ST = kAggTmaStages;
+  constexpr uint32_t ROWB = FP * sizeof(T);           // 512
+  constexpr uint32_t STAGE = 4 * ROWB;
+  extern __shared__ __align__(128) uint8_t agg_smem[];
+  uint8_t* base = agg_smem + ((128u - ((uint32_t)__cvta_generic_to_shared(agg_smem) & 127u)) & 127u);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* ring = base + warp * (ST * STAGE);
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(base + kTWarps * (ST * STAGE)) + warp * (ST * 8);
+  if (lane < ST) mbar_init(bar_u32 + lane * 8, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const int64_t row = (int64_t)blockIdx.x * kTWarps + warp;
+  if (row >= n_rows) return;                            // whole warps leave together
+  int64_t e = __ldg(rowptr + row);
+  const int64_t e1 = __ldg(rowptr + row + 1);
+  float acc[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) acc[t] = 0.f;
+  if (lr.rows != nullptr && e1 - e > kLongRow) {
+    const float* a = lr.acc + (int64_t)find_long_row(lr, row) * FP + lane * 8;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t] = a[t];
+    e = e1;
+  }
+  if (e < e1) {
+    const int n_e = (int)(e1 - e);
+    const int n_grp = (n_e + 3) >> 2;
+    // indices / weights in registers, 32 edges per coalesced load, broadcast by shuffle; padding edges gather row 0 with weight 0
+    float wcur = (lane < n_e) ? (val ? __ldg(val + e + lane) : 1.f) : 0.f;
+    int32_t cnext = (lane < n_e) ? __ldg(col + e + lane) : 0;
+    auto issue = [&](int grp, int stage) {
+      const int b = (grp * 4) & 31;
+      const int r0 = __shfl_sync(0xffffffffu, cnext, b), r1 = __shfl_sync(0xffffffffu, cnext, b + 1);
+      const int r2 = __shfl_sync(0xffffffffu, cnext, b + 2), r3 = __shfl_sync(0xffffffffu, cnext, b + 3);
+      if (lane == 0) {
+        mbar_expect_tx(bar_u32 + stage * 8, STAGE);
+        tma_gather4(ring_u32 + stage * STAGE, &tmap, r0, r1, r2, r3, bar_u32 + stage * 8);
+      }
+    };
+#pragma unroll
+    for (int st = 0; st < ST; ++st)
+      if (st < n_grp) issue(st, st);                    // ST * 4 <= 32: inside the first index chunk
+    for (int g = 0; g < n_grp; ++g) {
+      const int stage = g & (ST - 1);
+      if (((g * 4) & 31) == 0 && g) wcur = (g * 4 + lane < n_e) ? (val ? __ldg(val + e + g * 4 + lane) : 1.f) : 0.f;
+      mbar_wait(bar_u32 + stage * 8, (g / ST) & 1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float w = __shfl_sync(0xffffffffu, wcur, (g * 4 + u) & 31);
+        Slice8<T> v;
+        v.load_plain(reinterpret_cast<const T*>(ring + stage * STAGE + u * ROWB + lane * 16));
+        float f[8];
+        v.to_float(f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = fmaf(w, f[t], acc[t]);
+      }
+      __syncwarp();                                     // every lane has read the stage
+      const int j = g + ST;
+      if (j < n_grp) {
+        if (((j * 4) & 31) == 0) cnext = (j * 4 + lane < n_e) ? __ldg(col + e + j * 4 + lane) : 0;
+        issue(j, stage);
+      }
+    }
+  }
+  float self[8], d[8];
+  {
+    Slice8<T> s;
+    s.load(table + (row0 + row) * FP + lane * 8);
+    s.to_float(self);
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) d[t] = self[t] - acc[t];
+  Slice8<T>::store(z_out + row * FP + lane * 8, acc);
+  Slice8<T>::store(d_out + row * FP + lane * 8, d);
+}
+
 // Segment-parallel aggregation of the long rows: one lane group per segment of <= kLongRow
 // edges, partial sums added atomically into acc[long_index, :] (fp32, zeroed by the caller).
 // HALVES = 2: table rows are [L | H] pairs of FP features (row width 2*FP); 1: single FP-wide rows.
@@ -456,6 +545,20 @@ extern "C" int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row
   ACM_CHECK_ARG(rowptr && col && table && z_out && d_out, "spmm_agg_first: null pointer");
   if (n_rows == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == ACM_BF16 && fp == 256 && g_gather_mode == 3) {
+    // neighbour rows staged by the TMA engine (tile::gather4); row extent: see spmm_fwd.cu
+    CUtensorMap tm;
+    if (int rc = tma_encode_2d_u32(&tm, table, 128, 0x7fffffffull, 512, 128, 1, "input table")) return rc;
+    const int64_t blocks = (n_rows + kTWarps - 1) / kTWarps;
+    ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_agg_first: too many rows");
+    const size_t smem = (size_t)kTWarps * kAggTmaStages * (4 * 512 + 8) + 128;
+    cudaError_t e_ = cudaFuncSetAttribute(spmm_agg_first_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e_ != cudaSuccess) { set_error("spmm_agg_first: smem attribute: %s", cudaGetErrorString(e_)); return (int)e_; }
+    spmm_agg_first_tma_kernel<<<(unsigned)blocks, kTWarps * 32, smem, st>>>(
+        tm, n_rows, row0, rowptr, col, val, (const __nv_bfloat16*)table, (__nv_bfloat16*)z_out, (__nv_bfloat16*)d_out, lr);
+    ACM_LAUNCH_CHECK("spmm_agg_first (TMA gather)");
+    return 0;
+  }
 #define ACM_A_LAUNCH(TT)                                                                          \
   ACM_DISPATCH_FP(fp, {                                                                           \
     constexpr int RPB = (32 / (FP / 8)) * kTWarps;                                                \

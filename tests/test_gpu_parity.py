@@ -662,8 +662,45 @@ def test_gather_modes_agree_wide_rows(gather, mode):
         assert torch.isfinite(outs[0]).all()
         assert torch.equal(outs[0], outs[1])
     finally:
-        _lib.call("acm_set_gather_mode", 1)
+        _lib.call("acm_set_gather_mode", 3)
         os.environ.pop("ACMB200_REORDER", None)
+
+
+def test_tma_gather_aggregate_first_is_bit_identical(monkeypatch):
+    """Aggregate-first gather (Z = A.X) at input width 256 in bf16: neighbour rows staged by the TMA engine
+    (tile::gather4, gather mode 3) against the register-staged loop (mode 1) -- same accumulation order, so the output
+    and every gradient must be bitwise equal.  Degrees 1 .. > 100 exercise partial groups of four, the ring wrap-around
+    and the 32-edge index chunks; the last row block is partial."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    monkeypatch.setenv("ACMB200_REORDER", "auto")
+    monkeypatch.setenv("ACMB200_FUSED_FWD", "off")     # split-K-free path: deterministic forward, atomics only in dW
+    os.environ["ACMB200_DTYPE"] = "bf16"
+    n = 1501
+    row, col = O.synthetic_edges(n, 60000, seed=9)
+    hub = np.arange(1, 200)
+    row = np.concatenate([row, np.zeros_like(hub), hub])
+    col = np.concatenate([col, hub, np.zeros_like(hub)])
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    torch.manual_seed(4)
+    layer = A.GraphConvolution(256, 64, n, "acmgcn", variant=False).cuda()
+    x = torch.rand(n, 256, device="cuda")
+    outs = []
+    try:
+        for gm in (1, 3):
+            _lib.call("acm_set_gather_mode", gm)
+            timer = _lib.KernelTimer()
+            _lib.set_timer(timer)
+            try:
+                y = layer(x, op, None, None)
+                torch.cuda.synchronize()
+            finally:
+                _lib.set_timer(None)
+            assert any(k.startswith("acm_spmm_agg_first") for k in timer.spans)
+            outs.append(y.detach().clone())
+    finally:
+        _lib.call("acm_set_gather_mode", 3)
+    assert torch.isfinite(outs[0]).all() and torch.equal(outs[0], outs[1])
 
 
 @pytest.mark.parametrize("gather", ["0", "1", "2", "3"])
@@ -686,7 +723,7 @@ def test_gather_modes_agree(gather):
         assert torch.equal(out, ref)
         _close(out, g.z["out"], "fp32", "out")
     finally:
-        _lib.call("acm_set_gather_mode", 1)
+        _lib.call("acm_set_gather_mode", 3)
         os.environ.pop("ACMB200_REORDER", None)
 
 
