@@ -82,7 +82,7 @@ def load():
             fn.restype = _RESTYPES.get(name, _c.c_int)
         g = os.environ.get("ACMB200_GATHER")
         if g is not None:
-            lib.acm_set_gather_mode({"1": 1, "async": 1, "cp.async": 1, "2": 2, "bulk": 2, "3": 3, "tma": 3, "gather4": 3}.get(g.lower(), 0))
+            lib.acm_set_gather_mode({"1": 1, "async": 1, "cp.async": 1, "2": 2, "bulk": 2, "3": 3, "tma": 3, "gather4": 3, "4": 4, "tma-all": 4}.get(g.lower(), 0))
         h = os.environ.get("ACMB200_NARROW_HINT")
         if h is not None:
             lib.acm_set_narrow_row_hint(int(h))

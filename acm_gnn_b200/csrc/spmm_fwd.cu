@@ -618,7 +618,7 @@ static int launch_fwd(const FwdParams& p, cudaStream_t st) {
   // two lanes per row) the per-edge commit/wait overhead costs more than it hides (measured 5.4 vs
   // 4.8 ms), so they keep the register-staged LDG loop
   if constexpr (FP == 256 && sizeof(T) == 2) {
-    if (!p.pre_agg && g_gather_mode == 3) {
+    if (!p.pre_agg && g_gather_mode >= 3) {
       // north-star wording: neighbour rows staged in shared memory by the TMA engine (4 rows per request)
       CUtensorMap tm;
       // the row extent only bounds the coordinates the engine accepts: column ids are < the number of table rows by
@@ -707,8 +707,8 @@ extern "C" int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_
 }
 
 extern "C" int acm_set_gather_mode(int mode) {
-  if (mode < 0 || mode > 3) {
-    acm::set_error("gather mode must be 0 (LDG), 1 (cp.async ring), 2 (cp.async.bulk ring) or 3 (TMA tile::gather4)");
+  if (mode < 0 || mode > 4) {
+    acm::set_error("gather mode must be 0 (LDG), 1 (cp.async ring), 2 (cp.async.bulk ring), 3 (TMA tile::gather4) or 4 (3 + aggregate-first gather)");
     return ACM_ERR_BAD_ARG;
   }
   acm::g_gather_mode = mode;

@@ -353,6 +353,9 @@ spmm_agg_first_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ 
 // The same aggregation with the neighbour rows staged by the TMA engine (tile::gather4, four 512-byte rows per request
 // into a 4-stage ring of 2-KB stages per warp; see spmm_fwd.cu gather mode 3, where the technique beat the cp.async ring
 // 34.6 vs 37.4 ms).  Input width 256 in bf16: one row per warp, a lane owns 16 bytes of every row.
+// MEASURED SLOWER here: 24.4 vs 20.6 ms in the same run (profiles/r2_tma_gather_ab.txt).  With 512-byte rows a request
+// carries 2 KB instead of 4 KB, and at 52.5 M requests per launch the engine's request rate (~1 per 130 cycles per SM),
+// not the bytes, sets the pace.  Opt-in only (gather mode 4); the register-staged loop stays the default of this kernel.
 constexpr int kAggTmaStages = 4;
 __global__ void __launch_bounds__(kTWarps * 32)
 spmm_agg_first_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_rows, int64_t row0,
@@ -545,7 +548,7 @@ extern "C" int acm_spmm_agg_first(int dtype, int fp, int64_t n_rows, int64_t row
   ACM_CHECK_ARG(rowptr && col && table && z_out && d_out, "spmm_agg_first: null pointer");
   if (n_rows == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == ACM_BF16 && fp == 256 && g_gather_mode == 3) {
+  if (dtype == ACM_BF16 && fp == 256 && g_gather_mode == 4) {
     // neighbour rows staged by the TMA engine (tile::gather4); row extent: see spmm_fwd.cu
     CUtensorMap tm;
     if (int rc = tma_encode_2d_u32(&tm, table, 128, 0x7fffffffull, 512, 128, 1, "input table")) return rc;

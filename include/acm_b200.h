@@ -225,9 +225,11 @@ int acm_set_mix_bwd_ring(int on);
 /* Gather implementation of acm_spmm_mix_fwd: 1 (default) = cp.async ring in shared memory (each
  * lane keeps 8 neighbour rows in flight without register staging), 0 = LDG register staging,
  * 2 = cp.async.bulk ring (one 1-KB bulk copy per neighbour row, width 256 only; measured slower
- * than mode 1, kept as an opt-in), 3 = TMA row gather (cp.async.bulk.tensor ... tile::gather4: FOUR
- * neighbour rows per request of the TMA engine into a 3-stage shared-memory ring; width 256 in bf16
- * only, other shapes fall back to mode 1).  All modes give bit-identical results. */
+ * than mode 1, kept as an opt-in), 3 (default) = TMA row gather (cp.async.bulk.tensor ... tile::gather4:
+ * FOUR 1-KB neighbour rows per request of the TMA engine into a 2-stage shared-memory ring per warp;
+ * width 256 in bf16 -- measured 34.6 vs 37.4 ms for mode 1 on the headline graph; other shapes fall back to
+ * mode 1), 4 = 3 plus the same staging in acm_spmm_agg_first (512-byte rows: measured SLOWER, 24.4 vs
+ * 20.6 ms, opt-in).  All modes give bit-identical results. */
 int acm_set_gather_mode(int mode);
 
 /* Row-local backward of the attention/mix/relu part (autograd of layers.py:94-152,

@@ -668,7 +668,7 @@ def test_gather_modes_agree_wide_rows(gather, mode):
 
 def test_tma_gather_aggregate_first_is_bit_identical(monkeypatch):
     """Aggregate-first gather (Z = A.X) at input width 256 in bf16: neighbour rows staged by the TMA engine
-    (tile::gather4, gather mode 3) against the register-staged loop (mode 1) -- same accumulation order, so the output
+    (tile::gather4, opt-in gather mode 4) against the register-staged loop (mode 1) -- same accumulation order, so the output
     and every gradient must be bitwise equal.  Degrees 1 .. > 100 exercise partial groups of four, the ring wrap-around
     and the 32-edge index chunks; the last row block is partial."""
     import acm_gnn_b200 as A
@@ -683,11 +683,11 @@ def test_tma_gather_aggregate_first_is_bit_identical(monkeypatch):
     col = np.concatenate([col, hub, np.zeros_like(hub)])
     op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
     torch.manual_seed(4)
-    layer = A.GraphConvolution(256, 64, n, "acmgcn", variant=False).cuda()
+    layer = A.GraphConvolution(256, 128, n, "acmgcn", variant=False).cuda()
     x = torch.rand(n, 256, device="cuda")
     outs = []
     try:
-        for gm in (1, 3):
+        for gm in (1, 4):
             _lib.call("acm_set_gather_mode", gm)
             timer = _lib.KernelTimer()
             _lib.set_timer(timer)
