@@ -223,6 +223,115 @@ spmm_t_rank1_kernel(int64_t n_rows, int64_t row0, const int64_t* __restrict__ ro
   Slice8<T>::store(out + FP, accH);
 }
 
+// Transposed aggregation at width 256 in bf16 with the [dS_L|dS_H] rows (1 KB) staged by the TMA engine
+// (tile::gather4, 4 KB per request, 2-stage ring per warp, 3 CTAs per SM) -- the configuration that beat the cp.async
+// ring in the fused forward kernel (spmm_fwd.cu gather mode 3).  Same accumulation order as spmm_t_kernel: bit-identical.
+constexpr int kTTmaStages = 2;
+__global__ void __launch_bounds__(kTWarps * 32)
+spmm_t_tma_kernel(const __grid_constant__ CUtensorMap tmap, int64_t n_rows, int64_t row0, const int64_t* __restrict__ rowptr,
+                  const int32_t* __restrict__ col, const float* __restrict__ val, const __nv_bfloat16* __restrict__ table,
+                  const __nv_bfloat16* __restrict__ ptab, __nv_bfloat16* __restrict__ dh_all, const LongRows lr) {
+  using T = __nv_bfloat16;
+  constexpr int FP = 256, TW = 2 * FP;
+  constexpr int ST = kTTmaStages;
+  constexpr uint32_t ROWB = TW * sizeof(T);           // 1 KB
+  constexpr uint32_t STAGE = 4 * ROWB;
+  extern __shared__ __align__(128) uint8_t t_smem[];
+  uint8_t* base = t_smem + ((128u - ((uint32_t)__cvta_generic_to_shared(t_smem) & 127u)) & 127u);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint8_t* ring = base + warp * (ST * STAGE);
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t bar_u32 = (uint32_t)__cvta_generic_to_shared(base + kTWarps * (ST * STAGE)) + warp * (ST * 8);
+  if (lane < ST) mbar_init(bar_u32 + lane * 8, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  const int64_t row = (int64_t)blockIdx.x * kTWarps + warp;
+  if (row >= n_rows) return;
+  int64_t e = __ldg(rowptr + row);
+  const int64_t e1 = __ldg(rowptr + row + 1);
+  float accL[8], accH[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) accL[t] = accH[t] = 0.f;
+  if (lr.rows != nullptr && e1 - e > kLongRow) {
+    const float* a = lr.acc + (int64_t)find_long_row(lr, row) * TW + lane * 8;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      accL[t] = a[t];
+      accH[t] = a[FP + t];
+    }
+    e = e1;
+  }
+  if (e < e1) {
+    const int n_e = (int)(e1 - e);
+    const int n_grp = (n_e + 3) >> 2;
+    float wcur = (lane < n_e) ? (val ? __ldg(val + e + lane) : 1.f) : 0.f;
+    int32_t cnext = (lane < n_e) ? __ldg(col + e + lane) : 0;
+    auto issue = [&](int grp, int stage) {
+      const int b = (grp * 4) & 31;
+      const int r0 = __shfl_sync(0xffffffffu, cnext, b), r1 = __shfl_sync(0xffffffffu, cnext, b + 1);
+      const int r2 = __shfl_sync(0xffffffffu, cnext, b + 2), r3 = __shfl_sync(0xffffffffu, cnext, b + 3);
+      if (lane == 0) {
+        mbar_expect_tx(bar_u32 + stage * 8, STAGE);
+        tma_gather4(ring_u32 + stage * STAGE, &tmap, r0, r1, r2, r3, bar_u32 + stage * 8);
+      }
+    };
+#pragma unroll
+    for (int st = 0; st < ST; ++st)
+      if (st < n_grp) issue(st, st);
+    for (int g = 0; g < n_grp; ++g) {
+      const int stage = g & (ST - 1);
+      if (((g * 4) & 31) == 0 && g) wcur = (g * 4 + lane < n_e) ? (val ? __ldg(val + e + g * 4 + lane) : 1.f) : 0.f;
+      mbar_wait(bar_u32 + stage * 8, (g / ST) & 1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float w = __shfl_sync(0xffffffffu, wcur, (g * 4 + u) & 31);
+        Slice8<T> vl, vh;
+        vl.load_plain(reinterpret_cast<const T*>(ring + stage * STAGE + u * ROWB + lane * 16));
+        vh.load_plain(reinterpret_cast<const T*>(ring + stage * STAGE + u * ROWB + FP * sizeof(T) + lane * 16));
+        float fl[8], fh[8];
+        vl.to_float(fl);
+        vh.to_float(fh);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          accL[t] = fmaf(w, fl[t], accL[t]);
+          accH[t] = fmaf(w, fh[t], accH[t]);
+        }
+      }
+      __syncwarp();
+      const int j = g + ST;
+      if (j < n_grp) {
+        if (((j * 4) & 31) == 0) cnext = (j * 4 + lane < n_e) ? __ldg(col + e + j * 4 + lane) : 0;
+        issue(j, stage);
+      }
+    }
+  }
+  float self[8];
+  {
+    Slice8<T> s;
+    s.load(table + (row0 + row) * TW + FP + lane * 8);
+    s.to_float(self);
+  }
+#pragma unroll
+  for (int t = 0; t < 8; ++t) accH[t] = self[t] - accH[t];
+  if (ptab) {  // variant 1: relu sits before the aggregation -> mask with the forward table
+    Slice8<T> a, b;
+    float pl[8], ph[8];
+    a.load(ptab + row * TW + lane * 8);
+    b.load(ptab + row * TW + FP + lane * 8);
+    a.to_float(pl);
+    b.to_float(ph);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (!(pl[t] > 0.f)) accL[t] = 0.f;
+      if (!(ph[t] > 0.f)) accH[t] = 0.f;
+    }
+  }
+  T* out = dh_all + row * (3 * FP) + lane * 8;
+  Slice8<T>::store(out, accL);
+  Slice8<T>::store(out + FP, accH);
+}
+
 template <typename T, typename TO, int FP>
 __global__ void __launch_bounds__(kTWarps * 32)
 spmm_plain_kernel(int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -588,6 +697,20 @@ extern "C" int acm_spmm_t_bwd(int dtype, int fp, int64_t n_rows, int64_t row0,
   ACM_CHECK_ARG(rowptr_t && col_t && t_table && dh_all, "spmm_t_bwd: null pointer");
   if (n_rows == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == ACM_BF16 && fp == 256 && g_gather_mode >= 3) {
+    CUtensorMap tm;     // [dS_L|dS_H] table as uint32 [*, 256], box {256 x 1}; row extent: see spmm_fwd.cu
+    if (int rc = tma_encode_2d_u32(&tm, t_table, 256, 0x7fffffffull, 1024, 256, 1, "backward table")) return rc;
+    const int64_t blocks = (n_rows + kTWarps - 1) / kTWarps;
+    ACM_CHECK_ARG(blocks < (1ll << 31), "spmm_t_bwd: too many rows");
+    const size_t smem = (size_t)kTWarps * kTTmaStages * (4 * 1024 + 8) + 128;
+    cudaError_t e_ = cudaFuncSetAttribute(spmm_t_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e_ != cudaSuccess) { set_error("spmm_t_bwd: smem attribute: %s", cudaGetErrorString(e_)); return (int)e_; }
+    spmm_t_tma_kernel<<<(unsigned)blocks, kTWarps * 32, smem, st>>>(
+        tm, n_rows, row0, rowptr_t, col_t, val_t, (const __nv_bfloat16*)t_table, (const __nv_bfloat16*)p_table,
+        (__nv_bfloat16*)dh_all, lr);
+    ACM_LAUNCH_CHECK("spmm_t_bwd (TMA gather)");
+    return 0;
+  }
 #define ACM_T_LAUNCH(TT)                                                                           \
   ACM_DISPATCH_FP(fp, {                                                                            \
     constexpr int RPB = (32 / (FP / 8)) * kTWarps;                                                 \

@@ -666,6 +666,41 @@ def test_gather_modes_agree_wide_rows(gather, mode):
         os.environ.pop("ACMB200_REORDER", None)
 
 
+@pytest.mark.parametrize("variant", [False, True])
+def test_tma_gather_transposed_is_bit_identical(variant, monkeypatch):
+    """Transposed aggregation of the backward at width 256 in bf16: [dS_L|dS_H] rows staged by the TMA engine (gather
+    mode 3, default) against the register-staged loop (mode 1): dX and dW bitwise equal up to the dW atomics' order."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    monkeypatch.setenv("ACMB200_REORDER", "off")
+    monkeypatch.setenv("ACMB200_BWD_RANK1", "off")
+    os.environ["ACMB200_DTYPE"] = "bf16"
+    n = 1403
+    row, col = O.synthetic_edges(n, 50000, seed=11)
+    hub = np.arange(1, 300)                                # one long row (> 256 edges): the side pass feeds both kernels
+    row = np.concatenate([row, np.zeros_like(hub), hub])
+    col = np.concatenate([col, hub, np.zeros_like(hub)])
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    torch.manual_seed(8)
+    layer = A.GraphConvolution(64, 256, n, "acmgcn", variant=variant).cuda()
+    x = torch.rand(n, 64, device="cuda")
+    w = torch.randn(n, 256, device="cuda")
+    res = []
+    try:
+        for gm in (3, 1):
+            _lib.call("acm_set_gather_mode", gm)
+            layer.zero_grad(set_to_none=True)
+            xc = x.clone().requires_grad_(True)
+            y = layer(xc, op, None, None)
+            (y * w).sum().backward()
+            torch.cuda.synchronize()
+            res.append((y.detach().clone(), xc.grad.clone(), layer.weight_low.grad.clone()))
+    finally:
+        _lib.call("acm_set_gather_mode", 3)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    np.testing.assert_allclose(res[0][2].cpu().numpy(), res[1][2].cpu().numpy(), rtol=2e-3, atol=1e-5)
+
+
 def test_tma_gather_aggregate_first_is_bit_identical(monkeypatch):
     """Aggregate-first gather (Z = A.X) at input width 256 in bf16: neighbour rows staged by the TMA engine
     (tile::gather4, opt-in gather mode 4) against the register-staged loop (mode 1) -- same accumulation order, so the output
