@@ -170,7 +170,9 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
       ::"r"(dst), "l"(map), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
 }
-// host: uint32 2-D tensor map without swizzle (gemm_tc.cu)
+// host: cached tensor-map encoding (gemm_tc.cu).  kind 0 = bf16 elements with 128-byte swizzle, 1 = uint32 without swizzle
+int tma_encode_2d(CUtensorMap* map, int kind, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                  uint32_t box_inner, uint32_t box_outer, const char* what);
 int tma_encode_2d_u32(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                       uint32_t box_inner, uint32_t box_outer, const char* what);
 

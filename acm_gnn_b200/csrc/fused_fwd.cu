@@ -414,38 +414,9 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
 }
 
 // ---- host side --------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void* ptr = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
-  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !ptr) return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  return fn;
-}
-
 static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
                     uint32_t box_inner, uint32_t box_outer, const char* what) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { set_error("fused_agg_fwd: cuTensorMapEncodeTiled entry point unavailable"); return ACM_ERR_UNSUPPORTED; }
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch_elems * 2) % 16) {
-    set_error("fused_agg_fwd: %s must be 16-byte aligned with a row pitch that is a multiple of 16 bytes", what);
-    return ACM_ERR_BAD_ARG;
-  }
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {pitch_elems * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("fused_agg_fwd: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return ACM_ERR_BAD_ARG; }
-  return 0;
+  return tma_encode_2d(map, 0, ptr, inner, outer, pitch_elems * 2, box_inner, box_outer, what);   // cached (gemm_tc.cu)
 }
 
 }  // namespace fused

@@ -447,6 +447,12 @@ nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 // ---- host side ---------------------------------------------------------------------------
 
+}  // namespace tc
+
+// ---- tensor-map encoding, shared by every TMA user of the library (declared in acm_common.cuh) -------------------
+// A CUtensorMap is a pure function of (address, extents, pitch, box, element type, swizzle): the layer calls hand the
+// same buffers of the caching allocator back every step, so the encoded descriptors are kept in a small cache keyed by
+// exactly those values (SURVEY 8b "cached CUtensorMaps") instead of calling the driver 2-4 times per launch.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -462,24 +468,62 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor [outer][inner] with row pitch `pitch_elems`; box {box_inner, box_outer}; 128B swizzle; OOB -> 0
-static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
-                    uint32_t box_inner, uint32_t box_outer, const char* what) {
+namespace {
+struct MapKey {
+  const void* ptr; uint64_t inner, outer, pitch_bytes; uint32_t box_inner, box_outer; int kind;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && pitch_bytes == o.pitch_bytes &&
+           box_inner == o.box_inner && box_outer == o.box_outer && kind == o.kind;
+  }
+};
+constexpr int kMapCache = 64;
+struct MapCache {
+  MapKey key[kMapCache];
+  CUtensorMap map[kMapCache];
+  int used = 0, next = 0;
+};
+thread_local MapCache t_maps;    // per thread: no locking, the library is called from one host thread per device
+}  // namespace
+
+// kind 0: bf16 elements, 128-byte swizzle (GEMM operands); kind 1: uint32 elements, no swizzle (TMA row gather)
+int tma_encode_2d(CUtensorMap* map, int kind, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                  uint32_t box_inner, uint32_t box_outer, const char* what) {
+  const MapKey k{ptr, inner, outer, pitch_bytes, box_inner, box_outer, kind};
+  MapCache& c = t_maps;
+  for (int i = 0; i < c.used; ++i)
+    if (c.key[i] == k) { *map = c.map[i]; return 0; }
   EncodeTiledFn enc = get_encode();
-  if (!enc) { set_error("tcgen05 GEMM: cuTensorMapEncodeTiled entry point unavailable"); return ACM_ERR_UNSUPPORTED; }
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (pitch_elems * 2) % 16) {
-    set_error("tcgen05 GEMM: %s must be 16-byte aligned with a row pitch that is a multiple of 16 bytes", what);
+  if (!enc) { set_error("TMA: cuTensorMapEncodeTiled entry point unavailable"); return ACM_ERR_UNSUPPORTED; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || pitch_bytes % 16) {
+    set_error("TMA: %s must be 16-byte aligned with a row pitch that is a multiple of 16 bytes", what);
     return ACM_ERR_BAD_ARG;
   }
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(map, kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   kind == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("tcgen05 GEMM: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return ACM_ERR_BAD_ARG; }
+  if (r != CUDA_SUCCESS) { set_error("TMA: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return ACM_ERR_BAD_ARG; }
+  const int slot = c.used < kMapCache ? c.used++ : (c.next = (c.next + 1) % kMapCache);
+  c.key[slot] = k;
+  c.map[slot] = *map;
   return 0;
+}
+
+int tma_encode_2d_u32(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                      uint32_t box_inner, uint32_t box_outer, const char* what) {
+  return tma_encode_2d(map, 1, ptr, inner, outer, pitch_bytes, box_inner, box_outer, what);
+}
+
+namespace tc {
+
+// 2-D bf16 tensor [outer][inner] with row pitch `pitch_elems`; box {box_inner, box_outer}; 128B swizzle; OOB -> 0
+static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                    uint32_t box_inner, uint32_t box_outer, const char* what) {
+  return tma_encode_2d(map, 0, ptr, inner, outer, pitch_elems * 2, box_inner, box_outer, what);
 }
 
 static int pow2_cols(int n) { int c = 32; while (c < n) c <<= 1; return c; }
@@ -549,26 +593,6 @@ static int launch_tn(const void* a, int64_t lda, const void* b, int64_t ldb, con
 }
 
 }  // namespace tc
-
-// uint32 2-D tensor map without swizzle (the TMA row gather of spmm_fwd.cu: box {box_inner x box_outer})
-int tma_encode_2d_u32(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
-                      uint32_t box_inner, uint32_t box_outer, const char* what) {
-  tc::EncodeTiledFn enc = tc::get_encode();
-  if (!enc) { set_error("TMA: cuTensorMapEncodeTiled entry point unavailable"); return ACM_ERR_UNSUPPORTED; }
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || pitch_bytes % 16) {
-    set_error("TMA: %s must be 16-byte aligned with a row pitch that is a multiple of 16 bytes", what);
-    return ACM_ERR_BAD_ARG;
-  }
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {pitch_bytes};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("TMA: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r); return ACM_ERR_BAD_ARG; }
-  return 0;
-}
 
 int tc_gemm_fwd(const void* x, int64_t ldx, const void* wcat_t, void* h_lh, void* h_i, int64_t n, int64_t fin,
                 int64_t fp, int relu_lh, const PeerTables* peers, cudaStream_t st) {
