@@ -918,6 +918,10 @@ def run_ours(args):
 
 
 def main():
+    wd = os.environ.get("ACMB200_BENCH_WATCHDOG")
+    if wd:   # debugging aid for multi-GPU hangs: dump every thread's Python stack after N seconds and exit
+        import faulthandler
+        faulthandler.dump_traceback_later(float(wd), exit=True)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -55,7 +55,7 @@ for STEP in "$@"; do
       timeout 1200 python bench.py ${REST//,/ } > ${O}_bench_$i.log 2>&1; echo "=== [$STEP] rc=$?"; tail -3 ${O}_bench_$i.log | cut -c1-300 | grep -v '^{' ; python -c "$SUM" < ${O}_bench_$i.log ;;
     mbench)
       N=${REST%%:*}; A=""; [[ "$REST" == *:* ]] && A=${REST#*:}
-      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+i)) bench.py --gpus $N ${A//,/ } > ${O}_bench_g${N}_$i.log 2>&1
+      ACMB200_BENCH_WATCHDOG=${WATCHDOG:-240} timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+i)) bench.py --gpus $N ${A//,/ } > ${O}_bench_g${N}_$i.log 2>&1
       echo "=== [$STEP] rc=$?"; grep -iE "error|Traceback" ${O}_bench_g${N}_$i.log | head -5; python -c "$SUM" < ${O}_bench_g${N}_$i.log ;;
     dist)     # dist:N[:VAR=VALUE]  (e.g. dist:4:ACMB200_PUSH=0 for the NCCL exchange path)
       N=${REST%%:*}; E=""; [[ "$REST" == *:* ]] && E=${REST#*:}
