@@ -99,8 +99,16 @@ class RowPartition:
         if hit is not None:
             return hit
         import torch.distributed._symmetric_memory as symm
+        # First use of this table (warm-up steps only): allocate + rendezvous with IDLE devices and aligned hosts.
+        # The rendezvous maps peer memory and talks to the store while holding the GIL; doing that while this GPU
+        # still runs a kernel that waits for a peer (exchange barrier, NCCL) whose host is itself blocked in a later
+        # rendezvous can deadlock (seen once in ~15 two-GPU runs: rank 0 stuck before its all-reduce, rank 1 in the
+        # next rendezvous).  Draining the device and meeting at a barrier first removes every such interleaving.
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)
         t = symm.empty((self.world * self.rows_per_rank, width), dtype=dtype, device=device)
         hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+        torch.cuda.synchronize(device)
         ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in hdl.buffer_ptrs])
         mc = 0
         if os.environ.get("ACMB200_MULTICAST", "0") == "1":
