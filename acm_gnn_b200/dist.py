@@ -64,6 +64,8 @@ class RowPartition:
             if ok:
                 try:  # probe once: a tiny symmetric allocation + rendezvous (collective over the group)
                     import torch.distributed._symmetric_memory as symm
+                    torch.cuda.synchronize()            # rendezvous with drained devices and aligned hosts (see symm_table)
+                    dist.barrier(group=self.group)
                     t = symm.empty((1024,), dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
                     hdl = symm.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
                     ok = len(hdl.buffer_ptrs) == self.world
