@@ -20,7 +20,7 @@
 //   of every channel in quarters and exchange their three partial logits through shared memory.
 //   (A first version with two warps per quadrant that kept HI in 64 registers per thread was latency
 //   bound -- 8 warps, 3.5 k dependent instructions each per tile, issue slots 20 % busy: 11.7 ms against
-//   10.5 ms for the unfused launches, profiles/r2d_*.  Sixteen epilogue warps hide those latencies.)
+//   10.5 ms for the unfused launches, profiles/r2_fused_fwd_v1_ncu_*.  Sixteen epilogue warps hide those latencies.)
 //
 // Warps: 0 = TMA producer (4-stage ring of {A 128x64, B 256x64} bf16 tiles, 128B swizzle),
 //        1 = MMA issuer + TMEM owner, 2..17 = epilogue (warp w: lane quadrant w & 3, column quarter (w-2) >> 2).

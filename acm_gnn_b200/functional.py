@@ -396,8 +396,10 @@ class AcmLayerFunction(torch.autograd.Function):
         z = d = wcat_t = h_lh = None
         fused = False
         if agg_first:
-            h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev)
             # ---- aggregate-first: Z = A X, D = X - Z, then [S_L|S_H|HI] = [Z W_L | D W_H | X W_I] ----
+            fused = use_fused_forward(cfg, impl, fp, f, K, padded_width(fin))
+            # the fused kernel keeps [S_L|S_H] in TMEM: the table only exists in HBM when the backward needs it
+            h_lh = torch.empty(n, 2 * fp, dtype=tdt, device=dev) if (need_grad or not fused) else None
             if x_all is None:
                 x_all = xs if cfg.dist is None else cfg.dist.all_gather_rows(xs)
             z, d = _aggregate_input(op, x_all, n, ldx, tdt, cdt, st)
@@ -408,7 +410,6 @@ class AcmLayerFunction(torch.autograd.Function):
                 wp = torch.zeros(ldx, 3 * fp, dtype=tdt, device=dev)   # rows fin..ldx are zero
                 wp[:fin] = wcat
             wt = wcat_t_all  # [3fp, ldx], K-major (tcgen05 path) or None
-            fused = use_fused_forward(cfg, impl, fp, f, K, ldx)
             if not fused:
                 for k, (a_op, c_ptr, ldc) in enumerate(((z, h_lh.data_ptr(), 2 * fp),
                                                         (d, h_lh[:, fp:].data_ptr(), 2 * fp),
@@ -487,7 +488,7 @@ class AcmLayerFunction(torch.autograd.Function):
             # stay in TMEM, [S_L|S_H] and HI are written once (bf16) for the backward -- or not at all
             _lib.call("acm_fused_agg_fwd", z.data_ptr(), d.data_ptr(), xs.data_ptr(), ldx, wt.data_ptr(), ldx, pack.data_ptr(),
                       n, ldx, f, fp, float(cfg.out_scale), y.data_ptr(), _lib.ACM_BF16 if y_bf16 else _lib.ACM_F32, f,
-                      h_lh.data_ptr() if need_grad else 0, h_i.data_ptr(), att.data_ptr(), _lib.ptr(sig),
+                      _lib.ptr(h_lh), h_i.data_ptr(), att.data_ptr(), _lib.ptr(sig),
                       st, tag=fp)
         else:
             _lib.call("acm_spmm_mix_fwd", cdt, fp, f, n, row0, csr[0], csr[1], csr[2], 0,
