@@ -138,7 +138,26 @@ def use_rank1_table(cfg: LayerConfig, op, fp: int) -> bool:
         raise ValueError(f"ACMB200_BWD_RANK1={v!r}: expected auto, on or off")
     if v == "auto" and cfg.dist is None:
         return False
-    return bool(cfg.variant) and not cfg.ln_live and fp >= 64 and op.low.long_rows(True) is None
+    if not (bool(cfg.variant) and not cfg.ln_live and fp >= 64):
+        return False
+    return _no_long_rows_on_any_rank(op, cfg.dist)
+
+
+def _no_long_rows_on_any_rank(op, part) -> bool:
+    """The table layout is a protocol between the ranks (every rank writes rows into every other rank's table), so the
+    choice must be the same everywhere: the rank-1 table is used only when NO rank's slice of the transposed operator
+    has long rows.  Decided once per operator (one tiny all-reduce at its first backward)."""
+    flag = getattr(op, "_no_long_t_anywhere", None)
+    if flag is None:
+        local = op.low.long_rows(True) is None
+        if part is None:
+            flag = local
+        else:
+            t = torch.tensor([0.0 if local else 1.0], device=op.low.col.device)
+            part.all_reduce_(t)
+            flag = float(t.item()) == 0.0
+        op._no_long_t_anywhere = flag
+    return flag
 
 
 FUSED_FWD_DEFAULT = "auto"

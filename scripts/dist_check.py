@@ -42,12 +42,15 @@ def main():
              ("bf16", False, 4100, True, 0, 256, dict(OLD, **NS)), ("bf16", True, 3001, False, 1, 64, OLD),
              # rank-structured backward table (variant 1: G row + 4 scalars exchanged instead of [dO_L|dO_H]) is the
              # default under a partition; these keep the plain 2F-wide table push covered
-             ("bf16", True, 4100, False, 0, 256, {"ACMB200_BWD_RANK1": "off"}), ("fp32", True, 4096, False, 0, 64, {"ACMB200_BWD_RANK1": "off"})]
+             ("bf16", True, 4100, False, 0, 256, {"ACMB200_BWD_RANK1": "off"}), ("fp32", True, 4096, False, 0, 64, {"ACMB200_BWD_RANK1": "off"}),
+             # a hub node gives ONE rank a long row (> 256 edges) of the transposed operator: the table layout is a protocol
+             # between the ranks, so every rank must fall back to the plain table together (HUB marker, see below)
+             ("fp32", True, 4099, False, 0, 64, {"HUB": "1"}), ("bf16", True, 4099, True, 0, 256, {"HUB": "1"})]
     knobs = ("ACMB200_LOCAL_TABLE", "ACMB200_BWD_INPUT", "ACMB200_REORDER", "ACMB200_BWD_RANK1")
     for mode, variant, n, staged, struct, hid, env in cases:
         for k in knobs:
             os.environ.pop(k, None)
-        os.environ.update(env)
+        os.environ.update({k: v for k, v in env.items() if k.startswith("ACMB200_")})
         os.environ["ACMB200_DTYPE"] = mode
         fin, ncls = 48, 7
         g = torch.Generator(device=dev); g.manual_seed(5)
@@ -55,6 +58,10 @@ def main():
         dst = torch.randint(0, n, (40000,), generator=g, device=dev)
         keep = src != dst
         row, col = torch.cat([src[keep], dst[keep]]), torch.cat([dst[keep], src[keep]])
+        if env.get("HUB"):
+            hub = torch.arange(1, 400, device=dev)
+            row = torch.cat([row, torch.zeros_like(hub), hub])
+            col = torch.cat([col, hub, torch.zeros_like(hub)])
         key = torch.unique(row * n + col)
         row, col = key // n, key % n
         x = torch.rand(n, fin, generator=g, device=dev)

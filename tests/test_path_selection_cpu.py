@@ -13,7 +13,9 @@ from helpers import ROOT
 
 class _Csr:
     def __init__(self, long_rows=None):
+        import torch
         self._lr = long_rows
+        self.col = torch.zeros(1, dtype=torch.int32)       # device of the flag the ranks all-reduce
 
     def long_rows(self, transposed=False):
         return self._lr
@@ -63,7 +65,10 @@ def test_aggregate_first_and_input_backward_rules(monkeypatch):
 
 def test_partition_exchanges_the_narrower_operand(monkeypatch):
     from acm_gnn_b200.functional import LayerConfig, use_local_table, use_rank1_table
-    part = object()
+    class _Part:                      # stands in for dist.RowPartition: the other ranks report no long rows either
+        def all_reduce_(self, t):
+            return t
+    part = _Part()
     cfg = LayerConfig(dist=part, dtype="bf16")
     assert use_local_table(cfg, ldx=256, fp=256)          # X (256 wide) instead of [HL|HH] (512 wide)
     assert not use_local_table(cfg, ldx=256, fp=16)       # layer 1: the 32-wide table is the narrower one
