@@ -12,7 +12,7 @@ directory (it uses relative paths: ../data, splits/, ./logs) and runpy's the scr
 ``__main__``.  The reference files are executed as they are.
 
 Knobs (environment, so the reference CLI stays unchanged):
-    ACMB200_DTYPE = bf16 | fp32     storage of feature tables (default bf16)
+    ACMB200_DTYPE = fp32 | bf16     storage of feature tables (default fp32 = the reference precision; bf16 opts in)
     ACMB200_GEMM  = auto | simt | tcgen05
 """
 import importlib
