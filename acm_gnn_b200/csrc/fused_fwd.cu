@@ -157,7 +157,8 @@ __device__ __forceinline__ void ld_row32(const void* src, uint32_t* w) {
 
 // sum_j relu(acc[row, j]) * a[j] over this warp's CW columns of one channel (thread = row); the raw (pre-relu)
 // accumulators go to `dst` (this thread's row of the backward's table, bf16; nullptr: not stored) on the way
-__device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, __nv_bfloat16* dst) {
+template <bool KEEP>
+__device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, __nv_bfloat16* dst, uint32_t* keep = nullptr) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent FMA chains
 #pragma unroll
   for (int cc = 0; cc < CW / 32; ++cc) {
@@ -171,7 +172,15 @@ __device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, __nv_bf
       a2 = fmaf(fmaxf(v[j + 2], 0.f), av.z, a2);
       a3 = fmaf(fmaxf(v[j + 3], 0.f), av.w, a3);
     }
-    if (dst) {
+    if (KEEP) {       // the bf16 pairs stay in registers for the second pass (early release of the TMEM region)
+      uint32_t* w16 = keep + cc * 16;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w16[j] = pack2(v[2 * j], v[2 * j + 1]);
+      if (dst) {
+        st_row32(dst + cc * 32, w16);
+        st_row32(dst + cc * 32 + 16, w16 + 8);
+      }
+    } else if (dst) {
       uint32_t w16[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) w16[j] = pack2(v[2 * j], v[2 * j + 1]);
@@ -182,6 +191,11 @@ __device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, __nv_bf
   return (a0 + a1) + (a2 + a3);
 }
 
+// EARLY: the epilogue keeps bf16(S_H) of its columns in registers during the logit pass, so region R0 is released BEFORE
+// the second pass and the HI MMA of the next tile runs under it (in the late variant the epilogue warps spent 12 % of
+// their samples waiting for that MMA); the second pass then mixes bf16-rounded S_H -- the value the backward sees in the
+// table anyway, like HI.
+template <bool EARLY>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmD,
                      const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const Params p) {
@@ -197,8 +211,9 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
   const uint32_t bar_empty = bar_full + 8 * kStages;       // [kStages]
   const uint32_t bar_acc = bar_empty + 8 * kStages;        // [3]: HI, S_L, S_H accumulators complete
   const uint32_t bar_r0 = bar_acc + 24;                    // R0 drained (HI in registers)
-  const uint32_t bar_done = bar_r0 + 8;                    // epilogue finished with TMEM
-  const uint32_t tmem_slot = bar_done + 8;
+  const uint32_t bar_done = bar_r0 + 8;                    // epilogue finished with TMEM (EARLY: with R1)
+  const uint32_t bar_r0free = bar_done + 8;                // EARLY: epilogue finished with R0 (S_H kept in registers)
+  const uint32_t tmem_slot = bar_r0free + 8;
   float* s_a = reinterpret_cast<float*>(gbase + off_a);
   float* s_avec = reinterpret_cast<float*>(gbase + off_avec);
   float* s_z = reinterpret_cast<float*>(gbase + off_z);
@@ -214,6 +229,7 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     for (int c = 0; c < 3; ++c) mbar_init(bar_acc + 8 * c, 1);
     mbar_init(bar_r0, kEpiWarps);
     mbar_init(bar_done, kEpiWarps);
+    mbar_init(bar_r0free, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -264,11 +280,16 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       int t = 0;
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++t) {
         const uint32_t tp = (uint32_t)(t & 1);
-        mbar_wait(bar_done, tp ^ 1);       // the epilogue of the previous tile has released TMEM
+        // the epilogue of the previous tile has released TMEM: all of it (late) / region R0 (EARLY)
+        mbar_wait(EARLY ? bar_r0free : bar_done, tp ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
         for (int ch = 0; ch < 3; ++ch) {
-          if (ch == 2) {                   // S_H overwrites R0: HI must have been drained into registers
+          if (ch == 1 && EARLY) {          // S_L overwrites R1: the second pass of the previous tile must be over
+            mbar_wait(bar_done, tp ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          if (ch == 2) {                   // S_H overwrites R0: HI must have been drained
             mbar_wait(bar_r0, tp);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
@@ -304,7 +325,7 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       mbar_wait(bar_acc + 0, tp);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       __nv_bfloat16* hrow = p.h_i + (row_ok ? row : 0) * FP + c_lo;
-      const float zI = row_dot(lane_addr + (uint32_t)c_lo, s_a + 2 * FP + c_lo, row_ok ? hrow : nullptr);
+      const float zI = row_dot<false>(lane_addr + (uint32_t)c_lo, s_a + 2 * FP + c_lo, row_ok ? hrow : nullptr);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_r0);
@@ -313,14 +334,23 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
       __nv_bfloat16* trow = (p.s_lh && row_ok) ? p.s_lh + row * (2 * FP) + c_lo : nullptr;
       mbar_wait(bar_acc + 8, tp);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const float zL = row_dot(lane_addr + (uint32_t)(FP + c_lo), s_a + c_lo, trow);
+      const float zL = row_dot<false>(lane_addr + (uint32_t)(FP + c_lo), s_a + c_lo, trow);
       // this thread's HI values for the second pass: issued now, consumed after the S_H pass (L2 latency hidden)
-      uint32_t hi[CW / 2];
+      // (EARLY keeps bf16(S_H) in those registers instead and streams HI through a two-deep prefetch in the second pass)
+      uint32_t hi[EARLY ? 1 : CW / 2];
+      if (!EARLY) {
 #pragma unroll
-      for (int j = 0; j < CW / 16; ++j) ld_row32(hrow + j * 16, hi + j * 8);
+        for (int j = 0; j < CW / 16; ++j) ld_row32(hrow + j * 16, hi + j * 8);
+      }
       mbar_wait(bar_acc + 16, tp);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const float zH = row_dot(lane_addr + (uint32_t)c_lo, s_a + FP + c_lo, trow ? trow + FP : nullptr);
+      uint32_t sh[EARLY ? CW / 2 : 1];
+      const float zH = row_dot<EARLY>(lane_addr + (uint32_t)c_lo, s_a + FP + c_lo, trow ? trow + FP : nullptr, sh);
+      if (EARLY) {                         // R0 is free: the next tile's HI accumulation may start
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_r0free);
+      }
 
       // ---- combine the column parts (fixed order: identical sums in every warp of the quadrant), attention
       *reinterpret_cast<float4*>(s_z + ((tp * kParts + part) * BM + q * 32 + lane) * 4) = make_float4(zL, zH, zI, 0.f);
@@ -367,16 +397,27 @@ fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
 
       // ---- second pass: Y = c (att_L relu(S_L) + att_H relu(S_H) + att_I relu(HI)), 16 columns at a time
       // (columns >= f are padding with zero weights and are never stored; f % 16 == 0 for bf16 Y, % 8 for fp32)
+      uint32_t hp[2][8];                  // EARLY: HI of the current / next 16 columns
+      if (EARLY) ld_row32(hrow, hp[0]);
 #pragma unroll
       for (int hc = 0; hc < CW / 16; ++hc) {
         const int c0 = c_lo + hc * 16;
+        if (EARLY && hc + 1 < CW / 16) ld_row32(hrow + (hc + 1) * 16, hp[(hc + 1) & 1]);
         float vl[16], vh[16];
         tmem_ld16_issue(lane_addr + (uint32_t)(FP + c0), vl);
-        tmem_ld16_issue(lane_addr + (uint32_t)c0, vh);
+        if (!EARLY) tmem_ld16_issue(lane_addr + (uint32_t)c0, vh);
         tmem_wait_ld();
+        if (EARLY) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 s2 = unpack2(sh[hc * 8 + j]);
+            vh[2 * j] = s2.x;
+            vh[2 * j + 1] = s2.y;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float2 h2 = unpack2(hi[hc * 8 + j]);
+          const float2 h2 = unpack2(EARLY ? hp[hc & 1][j] : hi[hc * 8 + j]);
           vl[2 * j] = fmaf(cL, fmaxf(vl[2 * j], 0.f), fmaf(cH, fmaxf(vh[2 * j], 0.f), cI * fmaxf(h2.x, 0.f)));
           vl[2 * j + 1] = fmaf(cL, fmaxf(vl[2 * j + 1], 0.f), fmaf(cH, fmaxf(vh[2 * j + 1], 0.f), cI * fmaxf(h2.y, 0.f)));
         }
@@ -419,6 +460,8 @@ static int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t 
   return tma_encode_2d(map, 0, ptr, inner, outer, pitch_elems * 2, box_inner, box_outer, what);   // cached (gemm_tc.cu)
 }
 
+int g_fused_early = 0;   // acm_set_gemm_direct_store bit 2: early release of TMEM region R0 in the fused forward (A/B)
+
 }  // namespace fused
 }  // namespace acm
 
@@ -453,12 +496,13 @@ extern "C" int acm_fused_agg_fwd(const void* z, const void* d, const void* x, in
   if ((rc = make_map(&mx, x, (uint64_t)k, (uint64_t)n_rows, (uint64_t)ldx, BK, BM, "X"))) return rc;
   if ((rc = make_map(&mw, wcat_t, (uint64_t)k, (uint64_t)(3 * FP), (uint64_t)ldw, BK, FP, "Wcat^T"))) return rc;
   const size_t smem = (size_t)kStages * kStageBytes + 3 * FP * 4 + 64 + 2 * kParts * BM * 16 + 128 + 1024;
-  cudaError_t e = cudaFuncSetAttribute(fused_agg_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = g_fused_early ? fused_agg_fwd_kernel<true> : fused_agg_fwd_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("fused_agg_fwd: smem attribute (%zu bytes): %s", smem, cudaGetErrorString(e)); return (int)e; }
   int sms = 148, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t grid = p.m_tiles < sms ? p.m_tiles : sms;
-  fused_agg_fwd_kernel<<<(unsigned)grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mz, md, mx, mw, p);
+  kern<<<(unsigned)grid, kThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mz, md, mx, mw, p);
   ACM_LAUNCH_CHECK("fused_agg_fwd");
   return 0;
 }

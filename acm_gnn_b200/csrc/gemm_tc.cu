@@ -674,8 +674,11 @@ int tc_gemm_ab(const void* a, int64_t lda, const void* b_nk, int64_t ldb, void* 
 
 }  // namespace acm
 
+namespace acm { namespace fused { extern int g_fused_early; } }
+
 extern "C" int acm_set_gemm_direct_store(int on) {
   acm::tc::g_tn_direct = (on & 1) ? 1 : 0;
   acm::tc::g_tn_epi16 = (on & 2) ? 0 : 1;     // bit 1 set: keep 8 epilogue warps for short-K products too (A/B switch)
+  acm::fused::g_fused_early = (on & 4) ? 1 : 0;   // bit 2 set: early TMEM release in the fused forward (A/B switch)
   return 0;
 }

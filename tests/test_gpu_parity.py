@@ -468,9 +468,10 @@ def test_rank1_backward_table_matches_oracle(f, mode, monkeypatch):
             assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
 
 
+@pytest.mark.parametrize("early", [0, 1])
 @pytest.mark.parametrize("y_bf16", [False, True])
-@pytest.mark.parametrize("n,fin,f", [(1000, 256, 256), (4133, 48, 256), (129, 8, 200), (77, 100, 256)])
-def test_fused_tcgen05_forward_matches_unfused(n, fin, f, y_bf16, monkeypatch):
+@pytest.mark.parametrize("n,fin,f", [(1000, 256, 256), (4133, 48, 256), (129, 8, 200), (77, 100, 256), (40000, 64, 256)])
+def test_fused_tcgen05_forward_matches_unfused(n, fin, f, y_bf16, early, monkeypatch):
     """csrc/fused_fwd.cu (three tcgen05 GEMMs + attention/mix epilogue in one launch, accumulators in TMEM)
     against the unfused aggregate-first path (three GEMM launches that round [S_L|S_H|HI] to bf16 + epilogue
     launch) and against the oracle: forward within the bf16 tolerance, attention columns close, saved tables
@@ -480,6 +481,9 @@ def test_fused_tcgen05_forward_matches_unfused(n, fin, f, y_bf16, monkeypatch):
     from acm_gnn_b200 import _lib
     monkeypatch.setenv("ACMB200_REORDER", "auto")
     os.environ["ACMB200_DTYPE"] = "bf16"
+    # early = 1: the variant that releases TMEM region R0 before the second pass (bf16(S_H) kept in registers);
+    # 40 000 rows = 313 tiles over 148 CTAs: several tiles per CTA, so the cross-tile hand-over of both regions is exercised
+    _lib.call("acm_set_gemm_direct_store", 1 | (4 if early else 0))
     torch.manual_seed(n + fin)
     row, col = O.synthetic_edges(n, 12 * n, seed=n)
     op_ref = O.build_operator(row, col, n)
@@ -514,6 +518,7 @@ def test_fused_tcgen05_forward_matches_unfused(n, fin, f, y_bf16, monkeypatch):
         _close(res[knob][1], atto, "bf16", f"att ({knob})")
         for k, g in res[knob][2].items():
             _close_grad(g, p[k].grad, "bf16", f"d{k} ({knob})")
+    _lib.call("acm_set_gemm_direct_store", 1)
     # fused vs unfused: same math, the fused epilogue sees the fp32 accumulators instead of their bf16 rounding
     scale = float(res["off"][0].abs().max())
     assert float((res["auto"][0] - res["off"][0]).abs().max()) <= 2e-2 * scale
