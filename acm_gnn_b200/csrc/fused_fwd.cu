@@ -194,7 +194,9 @@ __device__ __forceinline__ float row_dot(uint32_t taddr, const float* a, __nv_bf
 // EARLY: the epilogue keeps bf16(S_H) of its columns in registers during the logit pass, so region R0 is released BEFORE
 // the second pass and the HI MMA of the next tile runs under it (in the late variant the epilogue warps spent 12 % of
 // their samples waiting for that MMA); the second pass then mixes bf16-rounded S_H -- the value the backward sees in the
-// table anyway, like HI.
+// table anyway, like HI.  MEASURED SLOWER: 8.65 / 8.69 ms against 7.98 ms for the late variant in the same run (the 32
+// extra live registers at the 96-register cap cost more in the second pass than the hidden MMA wait gives back).
+// Opt-in A/B switch (acm_set_gemm_direct_store bit 2); the late variant is the default.
 template <bool EARLY>
 __global__ void __launch_bounds__(kThreads, 1)
 fused_agg_fwd_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmD,

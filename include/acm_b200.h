@@ -213,7 +213,8 @@ int acm_spmm_mix_fwd(int dtype, int fp, int f, int64_t n_rows, int64_t row0,
  * pieces of its own output row with 256-bit stores straight from the TMEM registers whenever the output layout
  * allows (32-byte aligned rows, column counts in multiples of 16 bf16 / 8 fp32) and K >= 128; bit 0 clear = always go
  * through the shared-memory transposition tile.  Bit 1 set = keep 8 epilogue warps for store-bound short-K products
- * (default: 16 warps there).  A/B switches: bit-identical results in every setting. */
+ * (default: 16 warps there).  Bit 2 set = acm_fused_agg_fwd releases its first TMEM region before the second epilogue
+ * pass (measured slower, opt-in; mixes bf16-rounded S_H).  A/B switches: bits 0-1 give bit-identical results. */
 int acm_set_gemm_direct_store(int on);
 
 /* Register/occupancy trade-off of mix_bwd_kernel (plain 3-channel mode): 2 (default) or 3 resident
