@@ -34,6 +34,7 @@ def test_reference_train_py_cora_unchanged(dtype):
     splits is 88.62 +- 1.22 at convergence."""
     acc, out = _run(["--dataset_name", "cora", "--model", "acmgcn", "--epochs", "60", "--num_splits", "1",
                      "--fixed_splits", "1", "--hidden", "64"], dtype)
+    print(f"reference train.py on the drop-in, cora acmgcn [{dtype}]: test acc {acc:.4f}")
     assert acc >= 0.80, out[-2000:]
 
 
@@ -50,4 +51,5 @@ def test_reference_train_py_squirrel_acmgcnp_structure(dtype):
     acc, out = _run(["--dataset_name", "squirrel", "--model", "acmgcnp", "--structure_info", "1", "--variant", "0",
                      "--lr", "0.002", "--weight_decay", "1e-4", "--dropout", "0.6", "--epochs", "40",
                      "--num_splits", "1", "--fixed_splits", "1"], dtype)
+    print(f"reference train.py on the drop-in, squirrel acmgcnp + structure [{dtype}]: test acc {acc:.4f} (reference on CPU: 0.4938)")
     assert acc >= 0.45, out[-2000:]
