@@ -62,6 +62,25 @@ def _worker(rank, world, port, n, out_dir):
     gw = x[r0:r1].t() @ dh_loc
     part.all_reduce_(gw)
     assert torch.allclose(gw, gw_full, rtol=1e-4, atol=1e-6)
+    # ---- protocol decisions must be GLOBAL: only rank 0's slice has a long row -> every rank must refuse the
+    # rank-structured backward table (functional.use_rank1_table); with no long row anywhere every rank accepts it
+    from acm_gnn_b200.functional import LayerConfig, use_rank1_table
+
+    class _Csr:
+        def __init__(self, lr):
+            self.col, self._lr = torch.zeros(1, dtype=torch.int32), lr
+
+        def long_rows(self, transposed=False):
+            return self._lr
+
+    class _Op:
+        def __init__(self, lr):
+            self.low = _Csr(lr)
+
+    cfg = LayerConfig(variant=True, dist=part)
+    os.environ.pop("ACMB200_BWD_RANK1", None)
+    assert use_rank1_table(cfg, _Op(("rows",) if rank == 0 else None), 256) is False
+    assert use_rank1_table(cfg, _Op(None), 256) is True
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     dist.destroy_process_group()
 
