@@ -226,3 +226,48 @@ def test_degree_sorted_row_order_bit_identical(f, mode, monkeypatch):
         assert torch.equal(a[short], b[short])
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
     assert torch.allclose(res[0][1], res[1][1], rtol=1e-3, atol=1e-6)   # dX mixes rows through A^T
+
+
+def test_graphed_step_with_staged_input_update_and_operator_lifetime():
+    """(i) A StagedInput inside a captured step: new feature values reach the captured kernels only through
+    ``StagedInput.update_`` (which refreshes the kernel-layout copy in place).  (ii) The captured graph bakes the CSR
+    pointers of the operator in; the Graphed* classes resolve the operator once and keep it alive even when the
+    conversion cache evicts its own reference."""
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import operator as opmod
+    from acm_gnn_b200.functional import nll_log_softmax
+    from acm_gnn_b200.graphed import GraphedForward, GraphedTrainStep
+    g = Golden("gcn_pt_acmgcn_v0")
+    mode = "bf16"
+    model = _model_from_golden(g, mode)
+    opt = torch.optim.Adam(_train_params(model), lr=0.01, capturable=True)
+    low, high, un = g.adjacency()                      # the reference's own tensors (dense adj_low, COO adj_high)
+    low, high = low.cuda(), high.cuda()
+    x, labels = g.x.cuda(), g.labels.cuda()
+    mask = torch.zeros(g.n, dtype=torch.uint8, device="cuda")
+    mask[g.idx_train.cuda()] = 1
+    staged = A.stage_input(x.clone(), mode)
+    step = GraphedTrainStep(model, opt, staged, (low, high, None), labels, mask, warmup=2)
+    assert isinstance(step.adj[0], A.AcmOperator)      # resolved once, strong reference
+    opmod._CACHE.clear()                               # the cache forgets it; the graph must not care
+    junk = [torch.empty(1 << 20, device="cuda") for _ in range(8)]   # churn the allocator
+    del junk
+    l0 = float(step())
+    # eager reference of the same first step
+    ref = _model_from_golden(g, mode)
+    opt_r = torch.optim.Adam(_train_params(ref), lr=0.01, capturable=True)
+    opt_r.zero_grad(set_to_none=True)
+    loss_r = nll_log_softmax(ref(x, step.adj[0], None, None), labels, mask)
+    assert abs(l0 - float(loss_r)) <= 1e-3 * abs(float(loss_r)) + 1e-5
+    # new features: only update_ refreshes what the captured kernels read
+    fwd = GraphedForward(model, staged, (low, high, None))
+    out_a = fwd().clone()
+    x2 = torch.rand_like(x)
+    x2 = x2 / x2.sum(1, keepdim=True)
+    staged.update_(x2)
+    out_b = fwd().clone()
+    assert not torch.equal(out_a, out_b)
+    model.eval()
+    with torch.no_grad():
+        out_ref = model(A.stage_input(x2, mode), step.adj[0], None, None)
+    assert torch.allclose(out_b, out_ref, rtol=1e-3, atol=1e-4)
