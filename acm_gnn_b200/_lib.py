@@ -39,6 +39,8 @@ _PROTOS = {
     "acm_gemm_xw_fwd_push": [_vp, _i64, _vp, _vp, _i32, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp],
     "acm_spmm_t_bwd": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp],
     "acm_nll_log_softmax": [_vp, _i64, _i64, _i32, _vp, _vp, _f32, _vp, _vp, _i64, _vp],
+    "acm_glue_fwd": [_i32, _i32, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _vp, _vp],
+    "acm_glue_bwd": [_i32, _i32, _vp, _vp, _vp, _i64, _f32, _vp],
     "acm_set_l2_fetch_granularity": [_i32],
     "acm_set_gather_mode": [_i32],
     "acm_set_narrow_row_hint": [_i32],

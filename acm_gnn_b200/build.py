@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libacm_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["csr.cu", "gemm_simt.cu", "gemm.cu", "gemm_tc.cu", "fused_fwd.cu", "spmm_fwd.cu", "mix_bwd.cu", "spmm_t.cu", "loss.cu", "params.cu"]
+SOURCES = ["csr.cu", "gemm_simt.cu", "gemm.cu", "gemm_tc.cu", "fused_fwd.cu", "spmm_fwd.cu", "mix_bwd.cu", "spmm_t.cu", "loss.cu", "glue.cu", "params.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -728,3 +728,89 @@ def nll_log_softmax(out, labels, train_mask=None, n_train=None):
         sel = slice(None) if train_mask is None else train_mask.bool()
         return torch.nn.functional.nll_loss(lp[sel], labels[sel], reduction="sum") / float(n_train)
     return MaskedNllLogSoftmax.apply(out, labels, train_mask, 1.0 / float(n_train))
+
+
+# ---- inter-layer glue: relu -> dropout -> (+ xX) between the two layers ----------
+_GLUE_RNG = {}      # device index -> (torch seed it was derived from, int64[2] device tensor {seed, offset})
+
+
+def glue_rng_state(device):
+    """Device-resident {seed, offset} of the glue's Philox generator.  Seeded from torch's CUDA seed of
+    that device (so ``torch.manual_seed`` controls it) and re-seeded (offset 0) whenever that seed CHANGES
+    -- seeding torch again with the same value does not rewind it; the offset is advanced on the device by every dropout launch (graph replays draw fresh masks)."""
+    torch.cuda.init()                                   # runs a pending lazy torch.manual_seed
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    seed = int(torch.cuda.default_generators[idx].initial_seed())
+    cur = _GLUE_RNG.get(idx)
+    if cur is None or cur[0] != seed:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("inter_layer_glue: run one eager step before capturing (the generator state is created lazily)")
+        s = seed if seed < (1 << 63) else seed - (1 << 64)
+        cur = (seed, torch.tensor([s, 0], dtype=torch.int64, device=torch.device("cuda", idx)))
+        _GLUE_RNG[idx] = cur
+    return cur[1]
+
+
+class InterLayerGlue(torch.autograd.Function):
+    """y = dropout(relu(x), p) [+ add]: one launch forward (acm_glue_fwd: value + one pass bit per
+    element), one backward (acm_glue_bwd).  Replaces F.relu / F.dropout / "+" of
+    ACM-Pytorch/models/models.py:160-164."""
+
+    @staticmethod
+    def forward(ctx, x, add, relu, p):
+        xc = x.detach().contiguous()
+        ac = add.detach().contiguous() if add is not None else None
+        total = xc.numel()
+        need = ctx.needs_input_grad[0]
+        ydt = xc.dtype if ac is None else ac.dtype        # bf16 x + fp32 add -> fp32 (torch's promotion)
+        y = torch.empty(xc.shape, dtype=ydt, device=x.device)
+        mask = torch.empty((total + 7) // 8, dtype=torch.uint8, device=x.device) if need and (relu or p > 0) else None
+        state = glue_rng_state(x.device) if p > 0 else None
+        _lib.call("acm_glue_fwd", _dt_code(xc.dtype), _dt_code(ydt), xc.data_ptr(), _lib.ptr(ac), y.data_ptr(), _lib.ptr(mask),
+                  total, int(bool(relu)), float(p), _lib.ptr(state), _stream())
+        # the fp32 expression the kernel scaled by: 1.f / (1.f - p)
+        pf = ctypes.c_float(p).value
+        ctx.mask, ctx.xdt = mask, xc.dtype
+        ctx.scale = ctypes.c_float(1.0 / ctypes.c_float(1.0 - pf).value).value if p > 0 else 1.0
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if ctx.mask is None:
+                dx = g.to(ctx.xdt)
+            else:
+                gc = g.contiguous()
+                dx = torch.empty(gc.shape, dtype=ctx.xdt, device=gc.device)
+                _lib.call("acm_glue_bwd", _dt_code(ctx.xdt), _dt_code(gc.dtype), gc.data_ptr(), ctx.mask.data_ptr(), dx.data_ptr(),
+                          gc.numel(), ctx.scale, _stream())
+        return dx, (g if ctx.needs_input_grad[1] else None), None, None
+
+
+def _dt_code(dt):
+    return _lib.ACM_BF16 if dt == torch.bfloat16 else _lib.ACM_F32
+
+
+def inter_layer_glue(x, add=None, relu=True, p=0.0, training=True):
+    """``F.dropout(F.relu(x), p, training) + add`` -- the reference's glue between its two layers
+    (ACM-Pytorch/models/models.py:160-164, ACM-Geometric/models.py:70-74; ``relu=False`` when the relu
+    is the identity, ``add`` = the acmgcn++ ``xX`` branch).
+
+    With the dropout inactive (eval, or p == 0) the fused launch is bit-identical to the torch ops and is
+    the default.  With p > 0 in training the fused kernel draws its own Philox mask (same distribution,
+    NOT torch's random stream), so by default the reference's three torch ops run and results stay
+    reproducible against the reference under ``torch.manual_seed``; ``ACMB200_FUSED_DROPOUT=1`` opts in.
+    ``ACMB200_FUSED_GLUE=0`` keeps the torch ops everywhere."""
+    p_eff = float(p) if training and p >= 2.0 ** -32 else 0.0
+    if not relu and add is None and p_eff == 0.0:
+        return x
+    fusable = (x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and 0.0 <= p_eff < 1.0
+               and (add is None or (add.shape == x.shape and add.device == x.device
+                                    and (add.dtype == x.dtype or (add.dtype == torch.float32 and x.dtype == torch.bfloat16))))
+               and os.environ.get("ACMB200_FUSED_GLUE", "1") != "0"
+               and (p_eff == 0.0 or os.environ.get("ACMB200_FUSED_DROPOUT", "0") == "1"))
+    if not fusable:
+        y = torch.nn.functional.dropout(torch.relu(x) if relu else x, p, training=training)
+        return y if add is None else y + add
+    return InterLayerGlue.apply(x, add, bool(relu), p_eff)

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 from torch.nn.parameter import Parameter
 
 from . import layers as _layers_pt
-from .functional import StagedInput
+from .functional import StagedInput, inter_layer_glue
 from . import layers_geometric as _layers_geo
 
 
@@ -66,9 +66,8 @@ class GCN(nn.Module):
         if self.model_type == "acmgcnpp":
             xX = F.dropout(F.relu(self.mlpX(x_f32, input_tensor=True)), self.dropout, training=self.training)
         fea1 = self.gcns[0](x, adj_low, adj_high, adj_low_unnormalized)
-        if not (self.skip_identity_relu and not self.gcns[0].variant):
-            fea1 = F.relu(fea1)
-        fea1 = F.dropout(fea1, self.dropout, training=self.training)
-        if xX is not None:
-            fea1 = fea1 + xX
+        # relu -> dropout -> (+ xX) of models.py:160-164 in one launch per direction when that is
+        # bit-identical to the torch ops (functional.inter_layer_glue), the torch ops otherwise
+        relu = not (self.skip_identity_relu and not self.gcns[0].variant)
+        fea1 = inter_layer_glue(fea1, xX, relu, self.dropout, self.training)
         return self.gcns[1](fea1, adj_low, adj_high, adj_low_unnormalized)

@@ -292,6 +292,24 @@ int acm_nll_log_softmax(const float* logits, int64_t ld, int64_t n_rows, int n_c
                         const int64_t* labels, const uint8_t* mask, float scale,
                         float* loss_sum, float* dlogits, int64_t ld_d, void* stream);
 
+/* Inter-layer glue: y = dropout(relu(x), p) [+ add] in one pass, replacing the
+ * reference's F.relu / F.dropout / "+ xX" launches between the two layers
+ * (ACM-Pytorch/models/models.py:160-164, ACM-Geometric/models.py:70-74).  x, add (may be NULL), y:
+ * contiguous arrays of `total` elements of `dtype`, 16-byte aligned.  mask (may be NULL when no
+ * gradient is needed): ceil(total / 8) bytes, bit j of byte t = "element 8 t + j passes" (kept by
+ * the dropout AND, with relu, x > 0).  p in [0, 1); p > 0 draws Philox4x32-10 bits from the DEVICE
+ * state rng_state = {seed, offset} (element e kept iff philox(seed, [e / 4, offset])[e % 4] >=
+ * floor(p 2^32)) and advances the offset by one on the stream, so graph replays draw fresh masks.
+ * out_dtype = dtype, or ACM_F32 with dtype ACM_BF16 when `add` (and then y) is fp32 -- torch's type
+ * promotion of "bf16 activations + fp32 xX".  Not torch's random stream: the host mirror only uses
+ * p > 0 when asked to. */
+int acm_glue_fwd(int dtype, int out_dtype, const void* x, const void* add, void* y, uint8_t* mask,
+                 int64_t total, int relu, float p, uint64_t* rng_state, void* stream);
+/* dx = mask ? g * scale : 0   (scale = 1 / (1 - p)); the gradient of `add` is g itself.  g has
+ * out_dtype, dx has dtype (g is rounded to dtype first, as autograd's cast does). */
+int acm_glue_bwd(int dtype, int out_dtype, const void* g, const uint8_t* mask, void* dx, int64_t total,
+                 float scale, void* stream);
+
 /* cudaLimitMaxL2FetchGranularity (32/64/128 bytes) of the current device: narrow rows
  * (out_features <= 16 -> 64-byte table rows) over-fetch at the default granularity. */
 int acm_set_l2_fetch_granularity(int bytes);
