@@ -35,3 +35,29 @@ def test_argument_validation_without_gpu():
     assert b"dtype" in lib.acm_last_error_string()
     rc = lib.acm_cast_pad(0, 1, 1, 1, 0, 1, 4, 0)
     assert rc == 10001
+
+
+def test_ctypes_prototypes_match_the_header_argument_by_argument():
+    """Every ctypes prototype has the arity and the argument classes (pointer / 64-bit integer / int / float) of the
+    declaration in include/acm_b200.h -- a stale prototype would otherwise only show up as garbage on the GPU."""
+    import ctypes
+    from acm_gnn_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "acm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    decls = dict(re.findall(r"\b(acm_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src))
+    assert set(decls) == set(_lib._PROTOS)
+
+    def cls(param):
+        param = param.strip()
+        if "*" in param:
+            return ctypes.c_void_p
+        if re.match(r"(const\s+)?(int64_t|uint64_t)\b", param):
+            return ctypes.c_int64
+        if re.match(r"(const\s+)?float\b", param):
+            return ctypes.c_float
+        assert re.match(r"(const\s+)?(int|int32_t)\b", param), param
+        return ctypes.c_int
+
+    for name, params in decls.items():
+        want = [] if params.strip() in ("", "void") else [cls(p) for p in params.split(",")]
+        assert _lib._PROTOS[name] == want, f"{name}: header {[w.__name__ for w in want]} vs ctypes {[a.__name__ for a in _lib._PROTOS[name]]}"
