@@ -64,8 +64,10 @@ def test_glue_without_dropout_is_bit_identical_to_torch(dtypes, relu, with_add):
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
 def test_glue_dropout_mask_matches_philox_oracle_bit_for_bit(mode, monkeypatch):
     from acm_gnn_b200 import _lib
+    from acm_gnn_b200 import functional as Fn
     from acm_gnn_b200.functional import _stream, glue_rng_state, inter_layer_glue
     monkeypatch.setenv("ACMB200_FUSED_DROPOUT", "1")
+    Fn._GLUE_RNG.clear()                                    # independent of what ran before
     dt = torch.float32 if mode == "fp32" else torch.bfloat16
     p = 0.3
     torch.manual_seed(20261017)
@@ -116,7 +118,9 @@ def test_glue_dropout_mask_matches_philox_oracle_bit_for_bit(mode, monkeypatch):
 
 def test_glue_dropout_in_a_cuda_graph_draws_fresh_masks(monkeypatch):
     from acm_gnn_b200.functional import glue_rng_state, inter_layer_glue
+    from acm_gnn_b200 import functional as Fn
     monkeypatch.setenv("ACMB200_FUSED_DROPOUT", "1")
+    Fn._GLUE_RNG.clear()
     torch.manual_seed(11)
     x = torch.rand(2048, 64, device="cuda") + 0.5
     state = glue_rng_state(x.device)
