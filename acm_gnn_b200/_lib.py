@@ -48,6 +48,7 @@ _PROTOS = {
     "acm_set_mix_bwd_ring": [_i32],
     "acm_set_gemm_direct_store": [_i32],
     "acm_gemm_ab": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
+    "acm_linear_fwd": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp],
     "acm_gemm_atb": [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp],
     "acm_spmm_agg_first": [_i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
     "acm_fused_agg_fwd": [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _f32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _vp],

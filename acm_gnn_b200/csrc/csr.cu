@@ -102,7 +102,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, int64_t rows, int
 
 }  // namespace acm
 
-extern "C" int acm_version(void) { return 103; }  // 0.2.1: + acm_glue_fwd / acm_glue_bwd (102: acm_fused_agg_fwd, acm_spmm_t_bwd_rank1, table_mode of acm_mix_bwd)
+extern "C" int acm_version(void) { return 104; }  // 0.2.2: + acm_linear_fwd; 103: + acm_glue_fwd / acm_glue_bwd (102: acm_fused_agg_fwd, acm_spmm_t_bwd_rank1, table_mode of acm_mix_bwd)
 extern "C" const char* acm_last_error_string(void) { return acm::g_err; }
 extern "C" int64_t acm_launch_count(void) { return acm::g_launches.load(std::memory_order_relaxed); }
 

@@ -18,6 +18,8 @@ int tc_gemm_atb(const void* a, int64_t lda, const void* b, int64_t ldb, float* c
                 int64_t k_rows, int64_t m, int64_t ncols, cudaStream_t st);
 int tc_gemm_ab(const void* a, int64_t lda, const void* b_nk, int64_t ldb, void* c, int64_t ldc,
                int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st);
+int tc_gemm_linear(const void* x, int64_t ldx, const void* w_nk, int64_t ldw, const float* bias, void* y, int64_t ldy,
+                   int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st);
 }  // namespace acm
 
 extern "C" int acm_gemm_ab(int impl, int dtype, const void* a, int64_t lda, const void* b_kn, int64_t ldb_kn,
@@ -40,6 +42,17 @@ extern "C" int acm_gemm_ab(int impl, int dtype, const void* a, int64_t lda, cons
   p.m = m; p.n = n; p.k = k;
   p.c_bf16 = (dtype == ACM_BF16); p.relu_cols = relu ? (int)n : 0; p.atomic = 0;
   return gemm_simt(dtype, p, 1, st);
+}
+
+// nn.Linear (+ optional relu) of the reference's MLP helper (ACM-Pytorch/models/layers.py:245-285; the acmgcn++
+// branch xX = relu(mlpX(x)), models.py:116-122) on the tcgen05 path: bf16 operands, fp32 accumulation, fp32 bias.
+extern "C" int acm_linear_fwd(const void* x, int64_t ldx, const void* w_nk, int64_t ldw, const float* bias,
+                              void* y, int64_t ldy, int64_t m, int64_t n, int64_t k, int relu, void* stream) {
+  using namespace acm;
+  ACM_CHECK_ARG(x && w_nk && y, "linear_fwd: null pointer");
+  ACM_CHECK_ARG(m >= 0 && n >= 8 && n % 8 == 0 && k >= 8 && k % 8 == 0, "linear_fwd: need n %% 8 == 0 and k %% 8 == 0 (got n=%lld k=%lld)", (long long)n, (long long)k);
+  ACM_CHECK_ARG(ldx >= k && ldw >= k && ldy >= n && ldx % 8 == 0 && ldw % 8 == 0 && ldy % 8 == 0, "linear_fwd: row strides must be multiples of 8 elements and cover the rows");
+  return tc_gemm_linear(x, ldx, w_nk, ldw, bias, y, ldy, m, n, k, relu, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int acm_gemm_atb(int impl, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,

@@ -112,6 +112,8 @@ struct TnParams {
   int direct;
   // MODE 0: optional push of the c0 part ([HL|HH] rows) into every rank's table (peer memory)
   PeerTables peers;
+  // MODE 0: optional fp32 bias per output column, added before the relu (nn.Linear of the MLP helper)
+  const float* bias;
 };
 
 constexpr int kStgLd = 36;                           // staging row stride in words (32 + 4 pad)
@@ -241,6 +243,7 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                   float x0 = __uint_as_float(r[g2 * 16 + 2 * u]), x1 = __uint_as_float(r[g2 * 16 + 2 * u + 1]);
+                  if (p.bias) { x0 += __ldg(p.bias + j + 2 * u); x1 += __ldg(p.bias + j + 2 * u + 1); }
                   if (relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
                   w[u] = pack2_bf16(x0, x1);
                 }
@@ -276,6 +279,10 @@ tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const float4 v0 = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cc);
             const float4 v1 = *reinterpret_cast<const float4*>(stg + rr * kStgLd + cc + 4);
             float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            if (p.bias) {                                  // n % 8 == 0: the 8 columns are all valid
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] += __ldg(p.bias + j + u);
+            }
             if (j < p.relu_cols) {
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] = fmaxf(v[u], 0.f);
@@ -670,6 +677,18 @@ int tc_gemm_ab(const void* a, int64_t lda, const void* b_nk, int64_t ldb, void* 
   p.c1 = nullptr; p.ldc1 = 0;
   p.relu_cols = relu ? (int)n : 0;
   return tc::launch_tn<0>(a, lda, b_nk, ldb, p, st);
+}
+
+// y[m,n] (bf16) = relu?(x[m,k] . w[n,k]^T + bias[n])
+int tc_gemm_linear(const void* x, int64_t ldx, const void* w_nk, int64_t ldw, const float* bias, void* y, int64_t ldy,
+                   int64_t m, int64_t n, int64_t k, int relu, cudaStream_t st) {
+  tc::TnParams p{};
+  p.m = m; p.n = n; p.k = k;
+  p.c0 = (__nv_bfloat16*)y; p.ldc0 = ldy; p.ncols0 = (int)n;
+  p.c1 = nullptr; p.ldc1 = 0;
+  p.relu_cols = relu ? (int)n : 0;
+  p.bias = bias;
+  return tc::launch_tn<0>(x, ldx, w_nk, ldw, p, st);
 }
 
 }  // namespace acm

@@ -130,7 +130,16 @@ def attach(model, part: RowPartition):
     """Mark every ACM layer of ``model`` as row-partitioned (parameters stay replicated: all
     ranks seed identically, SURVEY.md 8e "Process model")."""
     from .layers import GraphConvolution
+    own = set()
     for m in model.modules():
         if isinstance(m, GraphConvolution):
             m.acm_dist = part
+            own.update(id(p) for p in m.parameters(recurse=False))
+    # Replicated parameters OUTSIDE the ACM layers (the mlpX branch of acmgcn++) see only this rank's rows: their
+    # gradients are partial sums like the layers' own (which AcmLayerFunction all-reduces itself) -> all-reduce them as
+    # autograd produces them.  (BatchNorm statistics of a deeper mlpX stay per rank.)
+    for h in getattr(model, "_acm_dist_hooks", []):
+        h.remove()
+    model._acm_dist_hooks = [p.register_hook(lambda g, part=part: part.all_reduce_(g.contiguous().clone()))
+                             for p in model.parameters() if id(p) not in own and p.requires_grad]
     return model

@@ -814,3 +814,67 @@ def inter_layer_glue(x, add=None, relu=True, p=0.0, training=True):
         y = torch.nn.functional.dropout(torch.relu(x) if relu else x, p, training=training)
         return y if add is None else y + add
     return InterLayerGlue.apply(x, add, bool(relu), p_eff)
+
+
+# ---- nn.Linear of the acmgcn++ mlpX branch on the tcgen05 path (bf16 storage mode) --------------------
+class LinearBf16(torch.autograd.Function):
+    """y = relu?(xs . W^T + b) in bf16 storage with fp32 accumulation (acm_linear_fwd), for an input that needs no
+    gradient (the layer-0 features); dW = dY^T xs (acm_gemm_atb), db = column sums of dY."""
+
+    @staticmethod
+    def forward(ctx, xs, weight, bias, relu):
+        m, ldx = xs.shape
+        n, fin = weight.shape
+        w = weight.detach()
+        if ldx == fin:
+            w_nk = w.to(torch.bfloat16).contiguous()
+        else:
+            w_nk = torch.zeros(n, ldx, dtype=torch.bfloat16, device=w.device)
+            w_nk[:, :fin] = w
+        b = bias.detach().float().contiguous() if bias is not None else None
+        y = torch.empty(m, n, dtype=torch.bfloat16, device=xs.device)
+        _lib.call("acm_linear_fwd", xs.data_ptr(), ldx, w_nk.data_ptr(), ldx, _lib.ptr(b), y.data_ptr(), n, m, n, ldx,
+                  int(bool(relu)), _stream(), tag=f"{ldx}x{n}")
+        ctx.save_for_backward(xs, y if relu else None)
+        ctx.fin, ctx.relu, ctx.has_bias = fin, bool(relu), bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        xs, y = ctx.saved_tensors
+        m, ldx = xs.shape
+        d = g.to(torch.bfloat16).contiguous()
+        if ctx.relu:
+            d = torch.ops.aten.threshold_backward(d, y, 0)          # g where y > 0
+        n = d.shape[1]
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dwp = torch.zeros(n, ldx, dtype=torch.float32, device=d.device)
+            _lib.call("acm_gemm_atb", _lib.GEMM_TCGEN05, _lib.ACM_BF16, d.data_ptr(), n, xs.data_ptr(), ldx, dwp.data_ptr(), ldx,
+                      m, n, ldx, _stream(), tag=f"linear{n}x{ldx}")
+            dw = dwp if ldx == ctx.fin else dwp[:, :ctx.fin].contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = d.sum(0, dtype=torch.float32)
+        return None, dw, db, None
+
+
+def linear_bf16_eligible(x, weight) -> bool:
+    """The tcgen05 Linear applies to a CUDA input that needs no gradient (raw or staged layer-0 features) with
+    out_features % 8 == 0 on an sm_100 device; everything else keeps torch's F.linear."""
+    if not (weight.is_cuda and tc_available() and weight.shape[0] % 8 == 0 and weight.dtype == torch.float32):
+        return False
+    if isinstance(x, StagedInput):
+        return x.dtype == "bf16" and x.xs.shape[1] >= weight.shape[1]
+    return x.is_cuda and x.dim() == 2 and not x.requires_grad and x.dtype in (torch.float32, torch.bfloat16)
+
+
+def linear_bf16(x, weight, bias=None, relu=False):
+    """``F.relu?(F.linear(x, weight, bias))`` with bf16 operands / output and fp32 accumulation.  ``x``: a StagedInput
+    (its bf16 copy is used as it is) or a [N, Fin] tensor (cast and zero-padded to a multiple of 8 columns)."""
+    fin = weight.shape[1]
+    if isinstance(x, StagedInput):
+        xs = x.xs
+    else:
+        ldx = padded_width(fin) if fin <= 256 else (fin + 7) // 8 * 8
+        xs = _stage_rows(x, torch.bfloat16, _lib.ACM_BF16, ldx, _stream())
+    return LinearBf16.apply(xs, weight, bias, relu)

@@ -19,7 +19,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.nn.parameter import Parameter
 
-from .functional import AcmLayerFunction, LayerConfig, default_dtype, padded_width
+from .functional import (AcmLayerFunction, LayerConfig, StagedInput, default_dtype, linear_bf16, linear_bf16_eligible,
+                         padded_width)
 from .operator import AcmOperator, cached_operator
 
 device = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")  # same module-level global as the reference (layers.py:10-11)
@@ -154,13 +155,28 @@ class MLP(nn.Module):
             if i < num_layers - 1 or num_layers == 1:
                 self.bns.append(nn.BatchNorm1d(widths[i + 1]))
         self.dropout = dropout
+        self.acm_dtype = default_dtype()
 
     def reset_parameters(self):
         for m in list(self.lins) + list(self.bns):
             m.reset_parameters()
 
-    def forward(self, data, input_tensor=False):
+    def forward(self, data, input_tensor=False, relu_out=False):
+        """``relu_out`` (ours): fold the caller's ``F.relu`` of the result into the last Linear.
+
+        In bf16 storage mode (``ACMB200_DTYPE=bf16``) a Linear whose input needs no gradient -- the
+        single-Linear ``mlpX`` of acmgcn++ on the raw features -- runs on the tcgen05 GEMM with bf16
+        operands and an fp32 bias/relu epilogue (functional.linear_bf16) and returns bf16; in fp32 mode
+        (the default) it is torch's fp32 ``F.linear``, the reference's arithmetic."""
         x = data if input_tensor else data.graph["node_feat"]
         for lin, bn in zip(self.lins[:-1], self.bns):
-            x = F.dropout(bn(F.relu(lin(x), inplace=True)), p=self.dropout, training=self.training)
-        return self.lins[-1](x)
+            x = F.dropout(bn(F.relu(self._lin(lin, x), inplace=True)), p=self.dropout, training=self.training)
+        return self._lin(self.lins[-1], x, relu_out)
+
+    def _lin(self, lin, x, relu=False):
+        if self.acm_dtype == "bf16" and os.environ.get("ACMB200_LINEAR", "auto") != "off" and linear_bf16_eligible(x, lin.weight):
+            return linear_bf16(x, lin.weight, lin.bias, relu)
+        if isinstance(x, StagedInput):
+            x = x.x
+        y = lin(x)
+        return F.relu(y) if relu else y

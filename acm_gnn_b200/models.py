@@ -64,7 +64,9 @@ class GCN(nn.Module):
             x_f32 = x
         xX = None
         if self.model_type == "acmgcnpp":
-            xX = F.dropout(F.relu(self.mlpX(x_f32, input_tensor=True)), self.dropout, training=self.training)
+            # relu folded into the Linear's epilogue; a staged bf16 input is consumed as it is (bf16 mode)
+            xX = F.dropout(self.mlpX(x if isinstance(x, StagedInput) else x_f32, input_tensor=True, relu_out=True),
+                           self.dropout, training=self.training)
         fea1 = self.gcns[0](x, adj_low, adj_high, adj_low_unnormalized)
         # relu -> dropout -> (+ xX) of models.py:160-164 in one launch per direction when that is
         # bit-identical to the torch ops (functional.inter_layer_glue), the torch ops otherwise

@@ -144,6 +144,12 @@ int acm_gemm_bwd_dx(int impl, int dtype, const void* dh, const void* wcat, const
 int acm_gemm_ab(int impl, int dtype, const void* a, int64_t lda, const void* b_kn, int64_t ldb_kn,
                 const void* b_nk, int64_t ldb_nk, void* c, int64_t ldc,
                 int64_t m, int64_t n, int64_t k, int relu, void* stream);
+/* y[m,n] (bf16, row stride ldy) = relu?(x[m,k] . w_nk[n,k]^T + bias[n]): the nn.Linear (+ F.relu) of the reference's
+ * MLP helper (ACM-Pytorch/models/layers.py:245-285; the acmgcn++ branch xX = relu(mlpX(x)), models.py:116-122) on the
+ * tcgen05 path.  x, w_nk bf16 (w_nk is nn.Linear's own [out, in] layout), bias fp32 or NULL; n and k multiples of 8,
+ * row strides multiples of 8 elements.  Its weight gradient is acm_gemm_atb(dY, x). */
+int acm_linear_fwd(const void* x, int64_t ldx, const void* w_nk, int64_t ldw, const float* bias,
+                   void* y, int64_t ldy, int64_t m, int64_t n, int64_t k, int relu, void* stream);
 /* C[m,n] (fp32, row stride ldc, zeroed by caller, atomically accumulated) += A[k_rows,m]^T . B[k_rows,n] */
 int acm_gemm_atb(int impl, int dtype, const void* a, int64_t lda, const void* b, int64_t ldb,
                  float* c, int64_t ldc, int64_t k_rows, int64_t m, int64_t n, void* stream);

@@ -81,6 +81,18 @@ def _worker(rank, world, port, n, out_dir):
     os.environ.pop("ACMB200_BWD_RANK1", None)
     assert use_rank1_table(cfg, _Op(("rows",) if rank == 0 else None), 256) is False
     assert use_rank1_table(cfg, _Op(None), 256) is True
+    # ---- replicated parameters outside the ACM layers (the mlpX branch of acmgcn++) see only the local rows:
+    # dist.attach hooks their gradients into the all-reduce; the result equals the full-batch gradient
+    from acm_gnn_b200.dist import attach
+    torch.manual_seed(3)
+    full_m, part_m = torch.nn.Linear(fin, 4), torch.nn.Linear(fin, 4)
+    part_m.load_state_dict(full_m.state_dict())
+    full_m(x).relu().sum().backward()
+    attach(part_m, part)
+    attach(part_m, part)                                   # idempotent: re-attaching must not reduce twice
+    part_m(x[r0:r1]).relu().sum().backward()
+    assert torch.allclose(part_m.weight.grad, full_m.weight.grad, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(part_m.bias.grad, full_m.bias.grad, rtol=1e-5, atol=1e-6)
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([1]))
     dist.destroy_process_group()
 

@@ -1,0 +1,101 @@
+"""The nn.Linear of the acmgcn++ ``mlpX`` branch (ACM-Pytorch/models/layers.py:245-285, models.py:116-122) on the tcgen05
+path in bf16 storage mode (acm_linear_fwd; weight gradient through acm_gemm_atb).
+
+Checked against a float64 emulation of exactly what the kernel is specified to compute -- operands rounded to bf16,
+exact products, fp32 bias added before the relu, ONE rounding of the result to bf16 -- so the stated tolerance is the
+rounding of the output alone: |y - ref| <= 2^-8 |ref| + 1e-6 (half a bf16 ulp is 2^-9 |ref|; the fp32 accumulation order
+adds ~1e-6).  Gradients (fp32 accumulation of bf16 operands): relative Frobenius <= 1e-4 against float64.  The model-level
+test holds the whole bf16 stack with the tcgen05 Linear to the repo's bf16 tolerance (3e-2 of max|ref|) against the same
+stack with torch's fp32 F.linear."""
+import pytest
+import torch
+
+from helpers import O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("shape", [(5000, 128, 256), (1000, 100, 64), (333, 37, 8), (2000, 300, 256), (129, 256, 24)])
+def test_linear_bf16_matches_float64_emulation(shape, relu):
+    import acm_gnn_b200 as A
+    from acm_gnn_b200 import _lib
+    from acm_gnn_b200.functional import linear_bf16, linear_bf16_eligible
+    m, fin, n = shape
+    g = torch.Generator().manual_seed(m + fin + n)
+    x = torch.rand(m, fin, generator=g).cuda()
+    w = (torch.randn(n, fin, generator=g) * 0.2).cuda().requires_grad_(True)
+    b = (torch.randn(n, generator=g) * 0.2).cuda().requires_grad_(True)
+    assert linear_bf16_eligible(x, w)
+    n0 = _lib.launch_count()
+    y = linear_bf16(x, w, b, relu)
+    assert _lib.launch_count() > n0 and y.dtype == torch.bfloat16 and y.shape == (m, n)
+    xb, wb = x.bfloat16().double(), w.detach().bfloat16().double()
+    pre = xb @ wb.T + b.detach().double()
+    ref = pre.relu() if relu else pre
+    err = (y.double() - ref).abs()
+    assert bool((err <= 2.0 ** -8 * ref.abs() + 1e-6).all()), float((err - 2.0 ** -8 * ref.abs()).max())
+    go = torch.randn(m, n, generator=g).cuda().bfloat16()
+    y.backward(go)
+    d = torch.where(y > 0, go, torch.zeros((), dtype=go.dtype, device="cuda")) if relu else go
+    dw_ref, db_ref = d.double().T @ xb, d.double().sum(0)
+    assert float((w.grad.double() - dw_ref).norm()) <= 1e-4 * float(dw_ref.norm())
+    assert float((b.grad.double() - db_ref).norm()) <= 1e-4 * float(db_ref.norm()) + 1e-6
+    if fin <= 256:
+        # a staged input (bf16, padded to the power-of-two width) is consumed as it is: same bits
+        xs = A.stage_input(x, "bf16")
+        assert torch.equal(linear_bf16(xs, w.detach(), b.detach(), relu), y.detach())
+    # no bias
+    y2 = linear_bf16(x, w.detach(), None, relu)
+    ref2 = (xb @ wb.T).relu() if relu else xb @ wb.T
+    assert bool(((y2.double() - ref2).abs() <= 2.0 ** -8 * ref2.abs() + 1e-6).all())
+
+
+def test_mlp_keeps_torch_linear_in_fp32_mode_and_for_inputs_that_need_grad(monkeypatch):
+    from acm_gnn_b200 import _lib
+    from acm_gnn_b200.layers import MLP
+    x = torch.rand(200, 64, device="cuda")
+    for mode, needs_grad, fused in (("fp32", False, False), ("bf16", True, False), ("bf16", False, True)):
+        monkeypatch.setenv("ACMB200_DTYPE", mode)
+        torch.manual_seed(0)
+        mlp = MLP(64, 32, 32, num_layers=1, dropout=0).cuda()
+        xi = x.clone().requires_grad_(needs_grad)
+        n0 = _lib.launch_count()
+        y = mlp(xi, input_tensor=True)
+        assert (_lib.launch_count() > n0) == fused, (mode, needs_grad)
+        assert y.dtype == (torch.bfloat16 if fused else torch.float32)
+        ref = torch.nn.functional.linear(x, mlp.lins[0].weight, mlp.lins[0].bias)
+        assert torch.allclose(y.float(), ref, rtol=2e-2, atol=2e-2)
+    monkeypatch.setenv("ACMB200_LINEAR", "off")
+    mlp = MLP(64, 32, 32, num_layers=1, dropout=0).cuda()
+    n0 = _lib.launch_count()
+    assert mlp(x, input_tensor=True).dtype == torch.float32 and _lib.launch_count() == n0
+
+
+@pytest.mark.parametrize("staged", [False, True])
+def test_acmgcnpp_stack_with_tcgen05_linear_matches_torch_linear(staged, monkeypatch):
+    import acm_gnn_b200 as A
+    monkeypatch.setenv("ACMB200_DTYPE", "bf16")
+    n, e, fin, hid, ncls = 4000, 40000, 128, 64, 5
+    row, col = O.synthetic_edges(n, e, seed=4)
+    op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
+    g = torch.Generator().manual_seed(0)
+    x = O.row_normalise_features(torch.rand(n, fin, generator=g)).cuda()
+    labels = torch.randint(0, ncls, (n,), generator=g).cuda()
+    res = {}
+    for lin in ("auto", "off"):
+        monkeypatch.setenv("ACMB200_LINEAR", lin)
+        torch.manual_seed(7)
+        model = A.GCN(fin, hid, ncls, 2, n, 0.0, "acmgcnpp", 0, variant=True).cuda()
+        model.train()
+        out = model(A.stage_input(x, "bf16") if staged else x, op, None, None)
+        torch.nn.functional.nll_loss(torch.log_softmax(out, 1), labels).backward()
+        res[lin] = (out.detach(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+    a, b = res["auto"], res["off"]
+    assert float((a[0] - b[0]).abs().max()) <= 3e-2 * float(b[0].abs().max())
+    assert a[1].keys() == b[1].keys() and "mlpX.lins.0.weight" in a[1] and "mlpX.lins.0.bias" in a[1]
+    for k in a[1]:
+        ga, gb = a[1][k].double().ravel(), b[1][k].double().ravel()
+        fro = float((ga - gb).norm() / gb.norm().clamp_min(1e-300))
+        cos = float(ga @ gb / (ga.norm() * gb.norm()).clamp_min(1e-300))
+        assert fro <= 0.35 and cos >= 0.98, (k, fro, cos)          # the bf16 gradient bound of tests/test_gpu_parity.py
