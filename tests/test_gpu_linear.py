@@ -73,9 +73,13 @@ def test_mlp_keeps_torch_linear_in_fp32_mode_and_for_inputs_that_need_grad(monke
 
 
 @pytest.mark.parametrize("staged", [False, True])
-def test_acmgcnpp_stack_with_tcgen05_linear_matches_torch_linear(staged, monkeypatch):
+def test_acmgcnpp_stack_with_tcgen05_linear_is_as_close_to_fp32_as_with_torch_linear(staged, monkeypatch):
+    """Whole acmgcn++ stack (variant 1) in bf16 storage, tcgen05 Linear against torch's fp32 F.linear for mlpX, both
+    judged against the SAME stack in fp32 storage: output within the repo's bf16 tolerance (3e-2 of max|ref|); every
+    gradient at most 3x as far from the fp32 run as with torch's Linear (or within 0.1 relative Frobenius).  Two bf16 runs
+    are not compared with each other directly: the high-pass weight gradients are cancelling sums whose bf16 storage noise
+    is independent between runs (measured 0.7 relative Frobenius between two bf16 runs on this graph)."""
     import acm_gnn_b200 as A
-    monkeypatch.setenv("ACMB200_DTYPE", "bf16")
     n, e, fin, hid, ncls = 4000, 40000, 128, 64, 5
     row, col = O.synthetic_edges(n, e, seed=4)
     op = A.AcmOperator.from_edges(torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda(), n)
@@ -83,19 +87,26 @@ def test_acmgcnpp_stack_with_tcgen05_linear_matches_torch_linear(staged, monkeyp
     x = O.row_normalise_features(torch.rand(n, fin, generator=g)).cuda()
     labels = torch.randint(0, ncls, (n,), generator=g).cuda()
     res = {}
-    for lin in ("auto", "off"):
+    for key, mode, lin in (("truth", "fp32", "off"), ("auto", "bf16", "auto"), ("off", "bf16", "off")):
+        monkeypatch.setenv("ACMB200_DTYPE", mode)
         monkeypatch.setenv("ACMB200_LINEAR", lin)
         torch.manual_seed(7)
         model = A.GCN(fin, hid, ncls, 2, n, 0.0, "acmgcnpp", 0, variant=True).cuda()
         model.train()
-        out = model(A.stage_input(x, "bf16") if staged else x, op, None, None)
+        out = model(A.stage_input(x, mode) if staged else x, op, None, None)
         torch.nn.functional.nll_loss(torch.log_softmax(out, 1), labels).backward()
-        res[lin] = (out.detach(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
-    a, b = res["auto"], res["off"]
-    assert float((a[0] - b[0]).abs().max()) <= 3e-2 * float(b[0].abs().max())
-    assert a[1].keys() == b[1].keys() and "mlpX.lins.0.weight" in a[1] and "mlpX.lins.0.bias" in a[1]
-    for k in a[1]:
-        ga, gb = a[1][k].double().ravel(), b[1][k].double().ravel()
-        fro = float((ga - gb).norm() / gb.norm().clamp_min(1e-300))
-        cos = float(ga @ gb / (ga.norm() * gb.norm()).clamp_min(1e-300))
-        assert fro <= 0.35 and cos >= 0.98, (k, fro, cos)          # the bf16 gradient bound of tests/test_gpu_parity.py
+        res[key] = (out.detach().float(), {k: p.grad.double().ravel() for k, p in model.named_parameters() if p.grad is not None})
+    t = res["truth"]
+    scale = float(t[0].abs().max())
+    assert float((res["auto"][0] - t[0]).abs().max()) <= 3e-2 * scale
+    assert float((res["off"][0] - t[0]).abs().max()) <= 3e-2 * scale
+    assert t[1].keys() == res["auto"][1].keys() == res["off"][1].keys() and "mlpX.lins.0.weight" in t[1] and "mlpX.lins.0.bias" in t[1]
+    rows, bad = [], []
+    for k, gt in t[1].items():
+        ea = float((res["auto"][1][k] - gt).norm() / gt.norm().clamp_min(1e-300))
+        eo = float((res["off"][1][k] - gt).norm() / gt.norm().clamp_min(1e-300))
+        rows.append(f"{k}: tcgen05 {ea:.2e} torch {eo:.2e}")
+        if ea > max(3 * eo, 0.1):
+            bad.append(k)
+    print("acmgcn++ bf16 gradients, rel.fro vs the fp32 run [staged %s] -- %s" % (staged, "; ".join(rows)))
+    assert not bad, (bad, rows)
