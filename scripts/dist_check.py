@@ -46,6 +46,12 @@ def main():
              # a hub node gives ONE rank a long row (> 256 edges) of the transposed operator: the table layout is a protocol
              # between the ranks, so every rank must fall back to the plain table together (HUB marker, see below)
              ("fp32", True, 4099, False, 0, 64, {"HUB": "1"}), ("bf16", True, 4099, True, 0, 256, {"HUB": "1"})]
+    if os.environ.get("ACMB200_DIST_CHECK_PP") == "1":
+        # acmgcn++ (PP marker): the mlpX branch has replicated parameters OUTSIDE the ACM layers, whose gradients
+        # dist.attach hooks into the all-reduce.  Opt-in: added after the last multi-GPU session of round 2, so far
+        # covered by the gloo test only (tests/test_dist_cpu.py).
+        cases += [("fp32", True, 4100, False, 0, 64, {"PP": "1"}), ("bf16", True, 4100, True, 0, 256, {"PP": "1"}),
+                  ("bf16", False, 4100, False, 0, 256, {"PP": "1"})]
     knobs = ("ACMB200_LOCAL_TABLE", "ACMB200_BWD_INPUT", "ACMB200_REORDER", "ACMB200_BWD_RANK1")
     for mode, variant, n, staged, struct, hid, env in cases:
         for k in knobs:
@@ -69,7 +75,7 @@ def main():
         mask = (torch.rand(n, generator=g, device=dev) < 0.6).to(torch.uint8)
         ntr = int(mask.sum().item())
         op = A.AcmOperator.from_edges(row, col, n, with_raw=bool(struct))
-        mtype = "acmgcnp" if struct else "acmgcn"
+        mtype = "acmgcnpp" if env.get("PP") else ("acmgcnp" if struct else "acmgcn")
 
         def build():
             torch.manual_seed(42)
